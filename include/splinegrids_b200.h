@@ -1,0 +1,193 @@
+/*
+ * splinegrids_b200.h -- C ABI of libsplinegrids_b200.so
+ *
+ * Hand-written sm_100a CUDA kernels for the grid-evaluation hot path of SplineGrids.jl
+ * (per-dimension basis tables, evaluate!, evaluate_adjoint!, refinement-matrix application).
+ * Every entry point replaces one KernelAbstractions kernel launch of the reference; the
+ * kernel's argument list is the operator interface being mirrored (cited as path:line in the
+ * reference checkout).  INTEGRATION.md shows the Julia `ccall` binding for each.
+ *
+ * Conventions
+ *  - All data pointers are DEVICE pointers owned by the caller, in Julia's column-major layout
+ *    (first index fastest): eval (n_1..n_D, Nout), control points (c_1..c_D, Nout),
+ *    basis tables (n, p+1, mdo+1).  Pointer/size ARRAYS (e.g. `tables`, `n_samples`) are HOST arrays
+ *    of length nin.
+ *  - Index arrays (sample_indices, row_pointer, column_start, refinement_indices) hold 1-BASED
+ *    Int32 values exactly as the reference stores them in its user-visible fields.
+ *  - `_f32` / `_f64` suffix = Float32 / Float64 (`Tv`).  `Ti` is Int32 (the reference's default,
+ *    src/spline_dimension.jl:105); a host shim converts Int64 index arrays.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are
+ *    asynchronous on that stream; the reference synchronises after every launch
+ *    (`synchronize(backend)`), which the host shim reproduces with one stream synchronize.
+ *  - Return value: 0 = OK; >0 = cudaError_t; <0 = sg_status below.  Nothing throws, nothing
+ *    allocates caller-visible memory, there is no global mutable state besides the launch counter.
+ *  - There is NO CPU fallback: without a CUDA device every compute entry point returns an error.
+ */
+#ifndef SPLINEGRIDS_B200_H
+#define SPLINEGRIDS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SG_MAX_DIMS 8     /* maximum number of input dimensions Nin / array rank */
+#define SG_MAX_DEGREE 15  /* maximum spline degree per dimension */
+
+typedef enum {
+    SG_OK = 0,
+    SG_ERR_INVALID_ARGUMENT = -1, /* NULL pointer, size <= 0, degree/derivative out of range */
+    SG_ERR_UNSUPPORTED = -2,      /* nin > SG_MAX_DIMS, degree > SG_MAX_DEGREE */
+    SG_ERR_WORKSPACE = -3,        /* workspace too small / misaligned */
+    SG_ERR_NCCL = -4              /* NCCL unavailable or returned an error */
+} sg_status;
+
+/* ---- library info ---------------------------------------------------------------------- */
+int sg_version(void);                       /* major*10000 + minor*100 + patch */
+const char *sg_status_string(int status);   /* static string for a return value */
+/* Number of kernels this library has launched since the last reset (process-wide, atomic). */
+int64_t sg_launch_count(void);
+void sg_launch_count_reset(void);
+/* Force a kernel variant: 0 = automatic, 1 = generic kernels only, 2 = prefer tiled fast paths even
+ * below the size threshold.  Test/benchmark hook (thread-unsafe, process-wide). */
+void sg_set_kernel_policy(int policy);
+/* Name of the kernel variant chosen by the last sg_evaluate / sg_evaluate_adjoint call. */
+const char *sg_last_variant(void);
+
+/* ---- K9 expand_knot_vector_kernel -- src/util_kernels.jl:1-20, launcher src/knot_vector.jl:29-37
+ * knots_all[sum(mult)] <- knot_values[i] repeated multiplicities[i] times. */
+int sg_expand_knot_vector_f32(float *knots_all, const float *knot_values, const int32_t *multiplicities,
+                              int64_t n_values, void *stream);
+int sg_expand_knot_vector_f64(double *knots_all, const double *knot_values, const int32_t *multiplicities,
+                              int64_t n_values, void *stream);
+
+/* ---- K1 set_sample_indices_kernel -- src/util_kernels.jl:22-49, launcher src/utils.jl:19-29
+ * sample_indices[i] = clamp(#{k : !(t_i < knots_all[k]) for the leading run}, p+1, n_knots-p-1);
+ * binary search instead of the reference's linear scan, bit-identical result. */
+int sg_span_indices_f32(int32_t *sample_indices, const float *sample_points, int64_t n,
+                        const float *knots_all, int64_t n_knots, int degree, void *stream);
+int sg_span_indices_f64(int32_t *sample_indices, const double *sample_points, int64_t n,
+                        const double *knots_all, int64_t n_knots, int degree, void *stream);
+
+/* ---- K2 spline_dimension_kernel -- src/spline_dimension.jl:160-215, launcher :231-242
+ * eval[n, p+1, mdo+1] <- non-zero basis values and derivatives (Cox-de Boor, in registers; the
+ * reference's eval_prev scratch array is not needed).  Operation order follows the reference
+ * and contraction is disabled, so tables are bit-identical to an IEEE evaluation of :169-214. */
+int sg_basis_tables_f32(float *eval, const float *knots_all, int64_t n_knots, const float *sample_points,
+                        const int32_t *sample_indices, int64_t n, int degree, int max_derivative_order,
+                        void *stream);
+int sg_basis_tables_f64(double *eval, const double *knots_all, int64_t n_knots, const double *sample_points,
+                        const int32_t *sample_indices, int64_t n, int degree, int max_derivative_order,
+                        void *stream);
+
+/* ---- K1+K2 fused (one launch): what SplineDimension(...) does at src/spline_dimension.jl:153-154 */
+int sg_dimension_build_f32(int32_t *sample_indices, float *eval, const float *knots_all, int64_t n_knots,
+                           const float *sample_points, int64_t n, int degree, int max_derivative_order,
+                           void *stream);
+int sg_dimension_build_f64(int32_t *sample_indices, double *eval, const double *knots_all, int64_t n_knots,
+                           const double *sample_points, int64_t n, int degree, int max_derivative_order,
+                           void *stream);
+
+/* ---- K10 decompress_basis_function_eval_kernel -- src/util_kernels.jl:51-67, src/spline_dimension.jl:251-272
+ * out[n, n_basis] (caller zero-fills) <- eval[:, :, derivative_order+1] scattered to columns l-p..l. */
+int sg_decompress_f32(float *out, const float *eval, const int32_t *sample_indices, int64_t n,
+                      int64_t n_basis, int degree, int derivative_order, void *stream);
+int sg_decompress_f64(double *out, const double *eval, const int32_t *sample_indices, int64_t n,
+                      int64_t n_basis, int degree, int derivative_order, void *stream);
+
+/* ---- K11 insert_kernel -- src/util_kernels.jl:69-79, src/utils.jl:58-64
+ * out[len+1] <- v with x inserted at 1-based position i_insert. */
+int sg_insert_f32(float *out, const float *v, int64_t len, int64_t i_insert, float x, void *stream);
+int sg_insert_f64(double *out, const double *v, int64_t len, int64_t i_insert, double x, void *stream);
+int sg_insert_i32(int32_t *out, const int32_t *v, int64_t len, int64_t i_insert, int32_t x, void *stream);
+
+/* ---- K12 collect_indices_kernel -- src/util_kernels.jl:81-88, src/utils.jl:187-196
+ * indices[n, nin] (column-major Int32) <- array of n CartesianIndex{nin} (nin Int64 each, AoS). */
+int sg_collect_indices_i32(int32_t *indices, const int64_t *cartesian, int64_t n, int nin, void *stream);
+
+/* ---- K3 spline_eval_kernel -- src/spline_grid.jl:119-183, launcher evaluate! :200-230
+ * eval[J,o] = sum_I prod_d B_d[J_d, I_d, der_d+1] * cp[base(J)+I, o]  (optionally rational: weights != NULL
+ * multiplies each term by w[base+I] and divides by the weighted sum).  eval need not be initialised.
+ * tables[d]: (n_samples[d], degree[d]+1, mdo[d]+1);  indices[d]: n_samples[d] 1-based spans. */
+int sg_evaluate_f32(float *eval, int nin, const int64_t *n_samples, const int64_t *n_cp, int nout,
+                    const float *const *tables, const int32_t *const *indices, const int *degree,
+                    const int *mdo, const int *der, const float *cp, const float *weights_or_null,
+                    void *stream);
+int sg_evaluate_f64(double *eval, int nin, const int64_t *n_samples, const int64_t *n_cp, int nout,
+                    const double *const *tables, const int32_t *const *indices, const int *degree,
+                    const int *mdo, const int *der, const double *cp, const double *weights_or_null,
+                    void *stream);
+
+/* ---- K4 spline_eval_adjoint_kernel -- src/adjoint.jl:1-40, launcher evaluate_adjoint! :52-83
+ * cp[i,o] = sum_{J : i in window(J)} prod_d B_d[..] * eval[J,o]; the callee zero-fills cp first
+ * (src/adjoint.jl:61).  No global atomics when the per-dimension span indices are non-decreasing
+ * (always true for the reference's constructor, src/spline_dimension.jl:121-128); otherwise an
+ * atomic scatter kernel is used.  `weights_or_null` != NULL selects the transpose of the
+ * fixed-weights rational map (an extension: the reference has no NURBS adjoint, src/adjoint.jl:52-57).
+ * `workspace` may be NULL (the callee then uses cudaMallocAsync on `stream`), else at least
+ * sg_evaluate_adjoint_workspace_bytes(...) bytes, 256-byte aligned (`rational` = weights will be passed). */
+size_t sg_evaluate_adjoint_workspace_bytes(int nin, const int64_t *n_samples, const int64_t *n_cp, int nout,
+                                           const int *degree, int elem_size /* 4 or 8 */, int rational /* 0|1 */);
+int sg_evaluate_adjoint_f32(float *cp, int nin, const int64_t *n_samples, const int64_t *n_cp, int nout,
+                            const float *const *tables, const int32_t *const *indices, const int *degree,
+                            const int *mdo, const int *der, const float *eval, const float *weights_or_null,
+                            void *workspace, size_t workspace_bytes, void *stream);
+int sg_evaluate_adjoint_f64(double *cp, int nin, const int64_t *n_samples, const int64_t *n_cp, int nout,
+                            const double *const *tables, const int32_t *const *indices, const int *degree,
+                            const int *mdo, const int *der, const double *eval, const double *weights_or_null,
+                            void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- K5 refinement_matrix_array_mul_kernel -- src/refinement_matrix.jl:365-403, mult! :421-445
+ * (row window helpers src/refinement_matrix.jl:103-125, src/utils.jl:204-235)
+ * Y[I] = sum_{J in window(I)} B[J] * prod_{d refined} A_d[I_d, J_d].  ndims = rank of Y and B (incl. Nout).
+ * dims[r] (1-based) is the array dimension refined by matrix r; row_ptr[r]/col_start[r] have
+ * sizeY[dims[r]-1] entries, nzval[r] has nnz[r]. */
+int sg_refmat_mul_f32(float *Y, const float *B, int ndims, const int64_t *sizeY, const int64_t *sizeB, int n_ref,
+                      const int *dims, const int32_t *const *row_ptr, const int32_t *const *col_start,
+                      const float *const *nzval, const int64_t *nnz, void *stream);
+int sg_refmat_mul_f64(double *Y, const double *B, int ndims, const int64_t *sizeY, const int64_t *sizeB, int n_ref,
+                      const int *dims, const int32_t *const *row_ptr, const int32_t *const *col_start,
+                      const double *const *nzval, const int64_t *nnz, void *stream);
+
+/* ---- K6 refinement_matrix_array_mul_adjoint_kernel -- src/adjoint.jl:85-125, mult_adjoint! :127-152
+ * B = transpose-apply of K5 to Y; the callee zero-fills B first (src/adjoint.jl:135). */
+int sg_refmat_mul_adjoint_f32(float *B, const float *Y, int ndims, const int64_t *sizeY, const int64_t *sizeB,
+                              int n_ref, const int *dims, const int32_t *const *row_ptr,
+                              const int32_t *const *col_start, const float *const *nzval, const int64_t *nnz,
+                              void *stream);
+int sg_refmat_mul_adjoint_f64(double *B, const double *Y, int ndims, const int64_t *sizeY, const int64_t *sizeB,
+                              int n_ref, const int *dims, const int32_t *const *row_ptr,
+                              const int32_t *const *col_start, const double *const *nzval, const int64_t *nnz,
+                              void *stream);
+
+/* ---- K7 local_refinement_kernel -- src/control_points.jl:296-311 (loop :339-347)
+ * cp[idx[i,:], o] = values[i, o];  idx (n_active, nin) and values (n_active, nout) column-major. */
+int sg_scatter_active_f32(float *cp, int nin, const int64_t *n_cp, int nout, const int32_t *refinement_indices,
+                          const float *refinement_values, int64_t n_active, void *stream);
+int sg_scatter_active_f64(double *cp, int nin, const int64_t *n_cp, int nout, const int32_t *refinement_indices,
+                          const double *refinement_values, int64_t n_active, void *stream);
+
+/* ---- K8 local_refinement_adjoint_kernel -- src/adjoint.jl:154-170 (loop :185-193)
+ * values[i, o] = cp[idx[i,:], o]; cp[idx[i,:], o] = 0. */
+int sg_gather_zero_active_f32(float *refinement_values, float *cp, int nin, const int64_t *n_cp, int nout,
+                              const int32_t *refinement_indices, int64_t n_active, void *stream);
+int sg_gather_zero_active_f64(double *refinement_values, double *cp, int nin, const int64_t *n_cp, int nout,
+                              const int32_t *refinement_indices, int64_t n_active, void *stream);
+
+/* ---- multi-GPU: gradient all-reduce (new; the reference is single-device) -------------------
+ * One communicator per process/GPU.  `unique_id` is a 128-byte ncclUniqueId produced by
+ * sg_comm_unique_id on rank 0 and distributed by the host (MPI, torch.distributed store, files).
+ * NCCL is resolved at run time (dlopen of libnccl.so.2); SG_ERR_NCCL if it is not available. */
+typedef struct sg_comm sg_comm;
+int sg_comm_unique_id(void *unique_id_128_bytes);
+int sg_comm_create(sg_comm **comm, int world_size, int rank, const void *unique_id_128_bytes);
+int sg_comm_destroy(sg_comm *comm);
+int sg_allreduce_sum_f32(float *buf, int64_t count, sg_comm *comm, void *stream);
+int sg_allreduce_sum_f64(double *buf, int64_t count, sg_comm *comm, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPLINEGRIDS_B200_H */

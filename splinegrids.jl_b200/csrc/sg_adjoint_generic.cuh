@@ -1,0 +1,89 @@
+// sg_adjoint_generic.cuh -- atomics-free generic adjoint: gather form over per-control-point
+// sample ranges.  Requires non-decreasing span indices per dimension (checked ON DEVICE by the
+// prep kernel, no host synchronisation): with monotone spans the samples whose window contains
+// control index i form one contiguous range per dimension.
+#pragma once
+#include "sg_common.cuh"
+
+// span_start[d][s] (s = 0..n_cp+1, 1-based span s) = first sample j with index[j] >= s
+// (lower bound), so the samples of span s are [span_start[s], span_start[s+1]).
+template <typename T>
+struct SgSpanStarts {
+    int32_t *start[SG_MAX_DIMS];
+};
+
+template <typename T>
+__global__ void sg_adjoint_prep_kernel(const __grid_constant__ SgGridArgs<T> a, const __grid_constant__ SgSpanStarts<T> ss,
+                                       SgAdjointHeader *hdr)
+{
+    const int d = blockIdx.y;
+    const int64_t n = a.n_samples[d];
+    const int32_t *__restrict__ idx = a.index[d];
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = tid; j + 1 < n; j += stride)
+        if (idx[j] > idx[j + 1]) hdr->nonmonotone = 1;
+    for (int64_t s = tid; s <= a.n_cp[d] + 1; s += stride) {
+        int64_t lo = 0, hi = n;  // first j with idx[j] >= s
+        while (lo < hi) {
+            int64_t mid = (lo + hi) >> 1;
+            if (idx[mid] >= s) hi = mid; else lo = mid + 1;
+        }
+        ss.start[d][s] = (int32_t)lo;
+    }
+}
+
+// One thread per control point; gathers prod_d B_d[J_d, i_d - span(J_d) + p_d] * eval[J, o]
+// over J in prod_d [lo_d, hi_d).  RATIONAL: eval is pre-divided by denom[J] and the result
+// multiplied by w[i] (transpose of the fixed-weights rational map).
+template <typename T, bool RATIONAL>
+__global__ void __launch_bounds__(128) sg_adjoint_gather_kernel(T *__restrict__ cp, const __grid_constant__ SgGridArgs<T> a,
+                                                                const __grid_constant__ SgSpanStarts<T> ss,
+                                                                const SgAdjointHeader *hdr, const T *__restrict__ eval,
+                                                                const T *__restrict__ weights, const T *__restrict__ denom)
+{
+    if (hdr->nonmonotone) return;
+    const int64_t lin = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (lin >= a.cp_total) return;
+    int64_t i[SG_MAX_DIMS], lo[SG_MAX_DIMS], hi[SG_MAX_DIMS], J[SG_MAX_DIMS];
+    int64_t r = lin, n_terms = 1;
+    for (int d = 0; d < a.nin; ++d) {
+        i[d] = r % a.n_cp[d] + 1;  // 1-based control index
+        r /= a.n_cp[d];
+        const int p = a.degree[d];
+        int64_t s0 = i[d] > p + 1 ? i[d] : p + 1;
+        int64_t s1 = i[d] + p < a.n_cp[d] ? i[d] + p : a.n_cp[d];
+        lo[d] = ss.start[d][s0];
+        hi[d] = ss.start[d][s1 + 1];
+        J[d] = lo[d];
+        n_terms *= (hi[d] - lo[d]);
+    }
+    for (int o0 = 0; o0 < a.nout; o0 += SG_GEN_OCHUNK) {
+        T acc[SG_GEN_OCHUNK];
+#pragma unroll
+        for (int q = 0; q < SG_GEN_OCHUNK; ++q) acc[q] = T(0);
+        for (int d = 0; d < a.nin; ++d) J[d] = lo[d];
+        for (int64_t t = 0; t < n_terms; ++t) {
+            T b = T(1);
+            int64_t off = 0, st = 1;
+            for (int d = 0; d < a.nin; ++d) {
+                const int I = (int)(i[d] - sg_ldg(a.index[d] + J[d]) + a.degree[d]);
+                b *= sg_ldg(a.table[d] + J[d] + a.n_samples[d] * I);
+                off += J[d] * st;
+                st *= a.n_samples[d];
+            }
+            if (RATIONAL) b /= sg_ldg(denom + off);
+#pragma unroll
+            for (int q = 0; q < SG_GEN_OCHUNK; ++q)
+                if (o0 + q < a.nout) acc[q] += b * sg_ldg(eval + off + a.n_total * (o0 + q));
+            for (int d = 0; d < a.nin; ++d) {
+                if (++J[d] < hi[d]) break;
+                J[d] = lo[d];
+            }
+        }
+        const T w = RATIONAL ? sg_ldg(weights + lin) : T(1);
+#pragma unroll
+        for (int q = 0; q < SG_GEN_OCHUNK; ++q)
+            if (o0 + q < a.nout) cp[lin + a.cp_total * (o0 + q)] = RATIONAL ? acc[q] * w : acc[q];
+    }
+}

@@ -1,0 +1,109 @@
+// sg_common.cuh -- shared definitions for the sm_100a kernels of libsplinegrids_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "splinegrids_b200.h"
+
+#define SG_MAXW (SG_MAX_DEGREE + 1)
+#define SG_GEN_OCHUNK 4   // outputs accumulated in registers per pass over the window (generic kernels)
+
+// Process-wide count of kernel launches made by this library (sg_launch_count()).
+extern std::atomic<int64_t> g_sg_launches;
+extern int g_sg_policy;            // 0 auto, 1 generic only, 2 prefer fast paths
+extern const char *g_sg_last_variant;
+
+#define SG_CHECK_ARG(cond)                          \
+    do {                                            \
+        if (!(cond)) return SG_ERR_INVALID_ARGUMENT; \
+    } while (0)
+
+#define SG_CUDA(call)                           \
+    do {                                        \
+        cudaError_t e__ = (call);               \
+        if (e__ != cudaSuccess) return (int)e__; \
+    } while (0)
+
+// Count the launch and surface launch-configuration errors without synchronising.
+#define SG_AFTER_LAUNCH()                        \
+    do {                                         \
+        g_sg_launches.fetch_add(1);              \
+        cudaError_t e__ = cudaPeekAtLastError(); \
+        if (e__ != cudaSuccess) return (int)e__; \
+    } while (0)
+
+static inline cudaStream_t sg_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline unsigned sg_blocks(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// Grid description passed BY VALUE to the evaluation kernels (no H2D copy, no allocation).
+template <typename T>
+struct SgGridArgs {
+    int nin;
+    int nout;
+    int64_t n_samples[SG_MAX_DIMS];
+    int64_t n_cp[SG_MAX_DIMS];
+    int64_t cp_stride[SG_MAX_DIMS];   // element stride of control-point dim d
+    const T *table[SG_MAX_DIMS];      // already offset to the selected derivative slice: (n_d, p_d+1)
+    const int32_t *index[SG_MAX_DIMS];
+    int degree[SG_MAX_DIMS];
+    int64_t n_total;                  // prod n_samples
+    int64_t cp_total;                 // prod n_cp
+    int64_t n_window;                 // prod (p_d + 1)
+};
+
+template <typename T>
+static inline int sg_fill_grid_args(SgGridArgs<T> &a, int nin, const int64_t *n_samples, const int64_t *n_cp,
+                                    int nout, const T *const *tables, const int32_t *const *indices,
+                                    const int *degree, const int *mdo, const int *der)
+{
+    SG_CHECK_ARG(n_samples && n_cp && tables && indices && degree && mdo && der);
+    if (nin < 1 || nin > SG_MAX_DIMS) return SG_ERR_UNSUPPORTED;
+    SG_CHECK_ARG(nout >= 1);
+    a.nin = nin;
+    a.nout = nout;
+    a.n_total = 1;
+    a.cp_total = 1;
+    a.n_window = 1;
+    for (int d = 0; d < SG_MAX_DIMS; ++d) {
+        a.n_samples[d] = 1; a.n_cp[d] = 1; a.cp_stride[d] = 0; a.table[d] = nullptr; a.index[d] = nullptr; a.degree[d] = 0;
+    }
+    for (int d = 0; d < nin; ++d) {
+        SG_CHECK_ARG(n_samples[d] >= 1 && n_cp[d] >= 1 && tables[d] && indices[d]);
+        if (degree[d] < 0 || degree[d] > SG_MAX_DEGREE) return SG_ERR_UNSUPPORTED;
+        SG_CHECK_ARG(n_cp[d] >= degree[d] + 1);
+        SG_CHECK_ARG(mdo[d] >= 0 && der[d] >= 0 && der[d] <= mdo[d]);
+        a.n_samples[d] = n_samples[d];
+        a.n_cp[d] = n_cp[d];
+        a.cp_stride[d] = a.cp_total;
+        a.table[d] = tables[d] + (int64_t)der[d] * (degree[d] + 1) * n_samples[d];
+        a.index[d] = indices[d];
+        a.degree[d] = degree[d];
+        a.n_total *= n_samples[d];
+        a.cp_total *= n_cp[d];
+        a.n_window *= degree[d] + 1;
+    }
+    return SG_OK;
+}
+
+// Adjoint workspace header (first 256 bytes of the workspace)
+struct SgAdjointHeader {
+    int nonmonotone;  // set to 1 by the prep kernel if any dimension's span indices decrease
+    int pad[63];
+};
+
+// Read-only (non-coherent) load helper
+template <typename T>
+__device__ __forceinline__ T sg_ldg(const T *p) { return __ldg(p); }
+
+// rounding-exact (non-contracted) arithmetic, so K2 reproduces an IEEE evaluation of the reference
+__device__ __forceinline__ float sg_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double sg_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float sg_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double sg_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float sg_sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double sg_sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float sg_div(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double sg_div(double a, double b) { return __ddiv_rn(a, b); }

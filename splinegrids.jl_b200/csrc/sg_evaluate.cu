@@ -1,0 +1,185 @@
+// sg_evaluate.cu -- C ABI + dispatch for K3 (evaluate!) and K4 (evaluate_adjoint!).
+// Reference launch sites: src/spline_grid.jl:200-230, src/adjoint.jl:52-83.
+#include <algorithm>
+
+#include "sg_adjoint_generic.cuh"
+#include "sg_evaluate_generic.cuh"
+#include "sg_fast.cuh"
+
+static inline size_t sg_align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// ---------------------------------------------------------------------------------------------
+// K3
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static int sg_evaluate_impl(T *eval, int nin, const int64_t *n_samples, const int64_t *n_cp, int nout,
+                            const T *const *tables, const int32_t *const *indices, const int *degree,
+                            const int *mdo, const int *der, const T *cp, const T *weights, void *stream)
+{
+    SG_CHECK_ARG(eval && cp);
+    SgGridArgs<T> a;
+    int rc = sg_fill_grid_args(a, nin, n_samples, n_cp, nout, tables, indices, degree, mdo, der);
+    if (rc != SG_OK) return rc;
+    cudaStream_t st = sg_stream(stream);
+    if (g_sg_policy != 1) {
+        rc = sg_evaluate_fast<T>(eval, a, cp, weights, st);
+        if (rc != SG_ERR_UNSUPPORTED) return rc;  // SG_OK or a real error
+    }
+    const int threads = 256;
+    const unsigned blocks = sg_blocks(a.n_total, threads);
+    if (weights)
+        sg_evaluate_generic_kernel<T, true><<<blocks, threads, 0, st>>>(eval, a, cp, weights);
+    else
+        sg_evaluate_generic_kernel<T, false><<<blocks, threads, 0, st>>>(eval, a, cp, weights);
+    g_sg_last_variant = "evaluate_generic";
+    SG_AFTER_LAUNCH();
+    return SG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4
+// ---------------------------------------------------------------------------------------------
+struct SgAdjointLayout {
+    size_t header;               // offset 0
+    size_t starts[SG_MAX_DIMS];  // int32[n_cp+2] per dimension
+    size_t denom;                // T[n_total] (rational only), else 0
+    size_t fast;                 // scratch of the tiled fast path
+    size_t total;
+};
+
+static SgAdjointLayout sg_adjoint_layout(int nin, const int64_t *n_samples, const int64_t *n_cp, int nout,
+                                         const int *degree, int elem_size, bool rational)
+{
+    SgAdjointLayout L{};
+    size_t off = sg_align256(sizeof(SgAdjointHeader));
+    int64_t n_total = 1;
+    for (int d = 0; d < nin; ++d) {
+        L.starts[d] = off;
+        off += sg_align256((size_t)(n_cp[d] + 2) * sizeof(int32_t));
+        n_total *= n_samples[d];
+    }
+    L.denom = off;
+    if (rational) off += sg_align256((size_t)n_total * elem_size);
+    L.fast = off;
+    off += sg_align256(sg_adjoint_fast_scratch_bytes(nin, n_samples, n_cp, nout, degree, elem_size));
+    L.total = off;
+    return L;
+}
+
+extern "C" size_t sg_evaluate_adjoint_workspace_bytes(int nin, const int64_t *n_samples, const int64_t *n_cp,
+                                                      int nout, const int *degree, int elem_size, int rational)
+{
+    if (nin < 1 || nin > SG_MAX_DIMS || !n_samples || !n_cp || !degree) return 0;
+    return sg_adjoint_layout(nin, n_samples, n_cp, nout, degree, elem_size, rational != 0).total;
+}
+
+template <typename T>
+static int sg_evaluate_adjoint_impl(T *cp, int nin, const int64_t *n_samples, const int64_t *n_cp, int nout,
+                                    const T *const *tables, const int32_t *const *indices, const int *degree,
+                                    const int *mdo, const int *der, const T *eval, const T *weights,
+                                    void *workspace, size_t workspace_bytes, void *stream)
+{
+    SG_CHECK_ARG(eval && cp);
+    SgGridArgs<T> a;
+    int rc = sg_fill_grid_args(a, nin, n_samples, n_cp, nout, tables, indices, degree, mdo, der);
+    if (rc != SG_OK) return rc;
+    cudaStream_t st = sg_stream(stream);
+    const bool rational = weights != nullptr;
+    const size_t cp_bytes = (size_t)a.cp_total * nout * sizeof(T);
+
+    // Tiny problems: the reference's own algorithm (zero fill + atomic scatter), 2 launches.
+    const double terms = (double)a.n_total * (double)a.n_window * nout;
+    if (g_sg_policy != 2 && terms <= 262144.0) {
+        SG_CUDA(cudaMemsetAsync(cp, 0, cp_bytes, st));
+        const unsigned blocks = sg_blocks(a.n_total, 256);
+        if (rational)
+            sg_adjoint_scatter_kernel<T, true><<<blocks, 256, 0, st>>>(cp, a, nullptr, eval, weights);
+        else
+            sg_adjoint_scatter_kernel<T, false><<<blocks, 256, 0, st>>>(cp, a, nullptr, eval, weights);
+        g_sg_last_variant = "adjoint_scatter_small";
+        SG_AFTER_LAUNCH();
+        return SG_OK;
+    }
+
+    const SgAdjointLayout L = sg_adjoint_layout(nin, n_samples, n_cp, nout, degree, (int)sizeof(T), rational);
+    char *ws = static_cast<char *>(workspace);
+    bool own = false;
+    if (ws) {
+        if (workspace_bytes < L.total || (reinterpret_cast<uintptr_t>(ws) & 255)) return SG_ERR_WORKSPACE;
+    } else {
+        SG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ws), L.total, st));
+        own = true;
+    }
+    SgAdjointHeader *hdr = reinterpret_cast<SgAdjointHeader *>(ws + L.header);
+    SgSpanStarts<T> ss{};
+    int64_t max_len = 2;
+    for (int d = 0; d < nin; ++d) {
+        ss.start[d] = reinterpret_cast<int32_t *>(ws + L.starts[d]);
+        max_len = std::max(max_len, std::max(n_samples[d], n_cp[d] + 2));
+    }
+    rc = SG_OK;
+    do {
+        cudaError_t e = cudaMemsetAsync(hdr, 0, sizeof(SgAdjointHeader), st);
+        if (e != cudaSuccess) { rc = (int)e; break; }
+        dim3 pgrid((unsigned)std::min<int64_t>((max_len + 255) / 256, 64), nin);
+        sg_adjoint_prep_kernel<T><<<pgrid, 256, 0, st>>>(a, ss, hdr);
+        g_sg_launches.fetch_add(1);
+
+        if (g_sg_policy != 1) {
+            int frc = sg_evaluate_adjoint_fast<T>(cp, a, ss, hdr, eval, weights, ws + L.fast, st);
+            if (frc != SG_ERR_UNSUPPORTED) { rc = frc; break; }
+        }
+        // generic: zero fill (src/adjoint.jl:61) needed by the scatter branch only, but the branch is
+        // chosen on device, so always done.
+        e = cudaMemsetAsync(cp, 0, cp_bytes, st);
+        if (e != cudaSuccess) { rc = (int)e; break; }
+        T *denom = nullptr;
+        if (rational) {
+            // denom[J] = sum_I prod_d B_d * w[base+I]: a non-rational forward pass with cp := w, Nout := 1
+            denom = reinterpret_cast<T *>(ws + L.denom);
+            SgGridArgs<T> a1 = a;
+            a1.nout = 1;
+            sg_evaluate_generic_kernel<T, false><<<sg_blocks(a.n_total, 256), 256, 0, st>>>(denom, a1, weights, nullptr);
+            g_sg_launches.fetch_add(1);
+        }
+        const unsigned gblocks = sg_blocks(a.cp_total, 128);
+        const unsigned sblocks = sg_blocks(a.n_total, 256);
+        if (rational) {
+            sg_adjoint_gather_kernel<T, true><<<gblocks, 128, 0, st>>>(cp, a, ss, hdr, eval, weights, denom);
+            sg_adjoint_scatter_kernel<T, true><<<sblocks, 256, 0, st>>>(cp, a, hdr, eval, weights);
+        } else {
+            sg_adjoint_gather_kernel<T, false><<<gblocks, 128, 0, st>>>(cp, a, ss, hdr, eval, weights, denom);
+            sg_adjoint_scatter_kernel<T, false><<<sblocks, 256, 0, st>>>(cp, a, hdr, eval, weights);
+        }
+        g_sg_launches.fetch_add(2);
+        g_sg_last_variant = "adjoint_gather_generic";
+        e = cudaPeekAtLastError();
+        if (e != cudaSuccess) rc = (int)e;
+    } while (0);
+    if (own) {
+        cudaError_t e = cudaFreeAsync(ws, st);
+        if (rc == SG_OK && e != cudaSuccess) rc = (int)e;
+    }
+    return rc;
+}
+
+#define SG_DEFINE_EVAL_API(T, SUF)                                                                                   \
+    extern "C" int sg_evaluate_##SUF(T *eval, int nin, const int64_t *n_samples, const int64_t *n_cp, int nout,      \
+                                     const T *const *tables, const int32_t *const *indices, const int *degree,       \
+                                     const int *mdo, const int *der, const T *cp, const T *weights, void *stream)    \
+    {                                                                                                                \
+        return sg_evaluate_impl<T>(eval, nin, n_samples, n_cp, nout, tables, indices, degree, mdo, der, cp, weights, \
+                                   stream);                                                                          \
+    }                                                                                                                \
+    extern "C" int sg_evaluate_adjoint_##SUF(T *cp, int nin, const int64_t *n_samples, const int64_t *n_cp,          \
+                                             int nout, const T *const *tables, const int32_t *const *indices,        \
+                                             const int *degree, const int *mdo, const int *der, const T *eval,       \
+                                             const T *weights, void *workspace, size_t workspace_bytes,              \
+                                             void *stream)                                                           \
+    {                                                                                                                \
+        return sg_evaluate_adjoint_impl<T>(cp, nin, n_samples, n_cp, nout, tables, indices, degree, mdo, der, eval,  \
+                                           weights, workspace, workspace_bytes, stream);                             \
+    }
+
+SG_DEFINE_EVAL_API(float, f32)
+SG_DEFINE_EVAL_API(double, f64)

@@ -1,0 +1,193 @@
+"""``RefinementMatrix`` and its application ``mult!`` / ``mult_adjoint!`` -- mirrors
+src/refinement_matrix.jl and src/adjoint.jl:85-152 of the reference.
+
+The APPLICATION (K5/K6) runs on the device through the C ABI.  Construction, validation, the
+sparse product and ``collect`` are set-up-time operations (SURVEY.md section 8f "next"); they run on the host
+in numpy on the small index/value arrays, which are then mirrored to the device.
+"""
+from __future__ import annotations
+
+from typing import Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .arrays import NP_OF, float_type, is_colmajor, require_cuda
+from .config import after_launch
+from .validation import SplineGridsError, validate_mult_input
+
+C = _lib.C
+
+
+class RefinementMatrix:
+    """Banded-row sparse matrix: row ``i`` holds consecutive non-zeros
+    ``nzval[row_pointer[i] : row_pointer[i+1]-1]`` starting at column ``column_start[i]`` (all 1-based, as
+    stored by the reference, src/refinement_matrix.jl:19-57).
+
+    ``row_pointer`` / ``column_start`` / ``nzval`` are device tensors (Int32 / Tv); ``*_host`` are the
+    numpy mirrors used by the set-up algebra."""
+
+    def __init__(self, m: int, n: int, row_pointer, column_start, nzval, device=None, validate: bool = True):
+        rp = _host(row_pointer).astype(np.int32)
+        cs = _host(column_start).astype(np.int32)
+        nz = _host(nzval)
+        if nz.dtype not in (np.float32, np.float64):
+            nz = nz.astype(np.float64)
+        assert len(rp) == len(cs) == m
+        assert np.array_equal(rp, np.sort(rp))
+        self.m, self.n = int(m), int(n)
+        self.row_pointer_host, self.column_start_host, self.nzval_host = rp, cs, nz
+        if validate:
+            bad = self.invalid_rows()
+            if bad:
+                raise SplineGridsError(f"Invalid rows: [{', '.join(str(b) for b in bad)}].")
+        dev = require_cuda(device)
+        self.row_pointer = torch.from_numpy(rp).to(dev)
+        self.column_start = torch.from_numpy(cs).to(dev)
+        self.nzval = torch.from_numpy(nz).to(dev)
+
+    # -- structure helpers (src/refinement_matrix.jl:103-125) -----------------------------------
+    def _row_lengths(self) -> np.ndarray:
+        nxt = np.append(self.row_pointer_host[1:], len(self.nzval_host) + 1).astype(np.int64)
+        return nxt - self.row_pointer_host.astype(np.int64)
+
+    def column_ranges(self) -> Tuple[np.ndarray, np.ndarray]:
+        """(column_start, column_end) per row, 1-based inclusive."""
+        cs = self.column_start_host.astype(np.int64)
+        return cs, cs + self._row_lengths() - 1
+
+    def invalid_rows(self):
+        """``validate_refinement_matrix_kernel`` -- src/refinement_matrix.jl:134-181 (1-based rows)."""
+        cs, ce = self.column_ranges()
+        ok = ce >= cs
+        ok &= ~ok | ((cs >= 1) & (ce <= self.n))
+        ok[0] = (cs[0] == 1) and (self.row_pointer_host[0] == 1)
+        prev_ok = ok.copy()
+        prev_ok[1:] &= (cs[:-1] <= cs[1:]) & (cs[1:] <= ce[:-1] + 1)
+        prev_ok[1:] &= ~prev_ok[1:] | (ce[1:] >= ce[:-1])
+        return [int(i) + 1 for i in np.flatnonzero(~prev_ok)]
+
+    @property
+    def shape(self):
+        return (self.m, self.n)
+
+    def __len__(self):
+        return self.m * self.n
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return self.nzval.dtype
+
+    @property
+    def device(self):
+        return self.nzval.device
+
+    def __eq__(self, other):   # src/refinement_matrix.jl:62-70
+        return (isinstance(other, RefinementMatrix) and self.shape == other.shape
+                and np.array_equal(self.row_pointer_host, other.row_pointer_host)
+                and np.array_equal(self.column_start_host, other.column_start_host)
+                and np.array_equal(self.nzval_host, other.nzval_host))
+
+    def __getitem__(self, ij):  # src/refinement_matrix.jl:72-86 (1-based i, j)
+        i, j = ij
+        if not (1 <= i <= self.m and 1 <= j <= self.n):
+            raise SplineGridsError(f"Index ({i}, {j}) out of bounds for refinement matrix of size ({self.m}, {self.n}).")
+        cs, ce = self.column_ranges()
+        if cs[i - 1] <= j <= ce[i - 1]:
+            return self.nzval_host[self.row_pointer_host[i - 1] - 1 + j - cs[i - 1]]
+        return self.nzval_host.dtype.type(0)
+
+    def collect(self) -> np.ndarray:
+        """``collect(A)`` -- dense host matrix, src/refinement_matrix.jl:329-363."""
+        out = np.zeros((self.m, self.n), dtype=self.nzval_host.dtype)
+        cs, ce = self.column_ranges()
+        for i in range(self.m):
+            p = self.row_pointer_host[i] - 1
+            out[i, cs[i] - 1:ce[i]] = self.nzval_host[p:p + ce[i] - cs[i] + 1]
+        return out
+
+    def __matmul__(self, other: "RefinementMatrix") -> "RefinementMatrix":
+        """``A * B`` -- src/refinement_matrix.jl:273-327.  Row i of C spans the union of the windows of the
+        rows of B selected by row i of A (contiguous because B's row windows are monotone and touching);
+        terms are accumulated in ascending k like the reference kernel (:203-227)."""
+        A, B = self, other
+        if A.n != B.m:
+            raise ValueError("DimensionMismatch: Inner dimensions must match")
+        a0, a1 = A.column_ranges()
+        b0, b1 = B.column_ranges()
+        c0 = b0[a0 - 1]
+        c1 = b1[a1 - 1]
+        lens = c1 - c0 + 1
+        rp = np.concatenate(([1], 1 + np.cumsum(lens[:-1]))).astype(np.int32)
+        nz = np.zeros(int(lens.sum()), dtype=A.nzval_host.dtype)
+        for i in range(A.m):
+            row = nz[rp[i] - 1: rp[i] - 1 + lens[i]]
+            pa = A.row_pointer_host[i] - 1
+            for k in range(a0[i], a1[i] + 1):
+                pb = B.row_pointer_host[k - 1] - 1
+                lb = b1[k - 1] - b0[k - 1] + 1
+                s = b0[k - 1] - c0[i]
+                row[s:s + lb] += A.nzval_host[pa] * B.nzval_host[pb:pb + lb]
+                pa += 1
+        return RefinementMatrix(A.m, B.n, rp, c0.astype(np.int32), nz, device=A.device)
+
+    def __repr__(self):
+        return f"RefinementMatrix({self.m}x{self.n}, nnz={len(self.nzval_host)}, {self.dtype})"
+
+
+def _host(a) -> np.ndarray:
+    return a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+
+
+def rmeye(n: int, device=None, float_type_="Float32") -> RefinementMatrix:
+    """``rmeye`` -- identity refinement matrix, src/refinement_matrix.jl:463-474."""
+    r = np.arange(1, n + 1, dtype=np.int32)
+    return RefinementMatrix(n, n, r, r.copy(), np.ones(n, dtype=NP_OF[float_type(float_type_)]), device=device)
+
+
+def refinement_matrix_from_dense(A: np.ndarray, device=None) -> RefinementMatrix:
+    """``RefinementMatrix(A::Matrix)`` -- src/refinement_matrix.jl:476-504 (raises "Invalid rows: [...]")."""
+    A = np.asarray(A)
+    rp, cs, nz = [], [], []
+    pointer = 1
+    for row in A:
+        nzi = np.flatnonzero(row)
+        rp.append(pointer)
+        if len(nzi) == 0:
+            cs.append(0)
+        else:
+            cs.append(int(nzi[0]) + 1)
+            nz.append(row[nzi[0]:nzi[-1] + 1])
+            pointer += int(nzi[-1] - nzi[0]) + 1
+    nzv = np.concatenate(nz) if nz else np.zeros(0, dtype=A.dtype)
+    return RefinementMatrix(A.shape[0], A.shape[1], rp, cs, nzv, device=device)
+
+
+def _refmat_call(name: str, out: torch.Tensor, inp: torch.Tensor, Y: torch.Tensor, B: torch.Tensor,
+                 As: Sequence[RefinementMatrix], dims_refinement: Sequence[int]) -> None:
+    assert is_colmajor(Y) and is_colmajor(B), "mult!/mult_adjoint! need dense column-major arrays"
+    assert Y.dtype == B.dtype and all(A.dtype == Y.dtype for A in As)
+    n_ref = len(As)
+    with torch.cuda.device(Y.device):
+        fn = getattr(_lib.lib(), name + _lib.suffix(Y.dtype))
+        _lib.check(fn(_lib.ptr(out), _lib.ptr(inp), C.c_int(Y.dim()), _lib.i64_array(Y.shape), _lib.i64_array(B.shape),
+                      C.c_int(n_ref), _lib.int_array(dims_refinement),
+                      _lib.ptr_array([A.row_pointer for A in As]), _lib.ptr_array([A.column_start for A in As]),
+                      _lib.ptr_array([A.nzval for A in As]), _lib.i64_array([A.nzval.numel() for A in As]),
+                      _lib.stream_ptr(Y.device)), name.rstrip("_"))
+    after_launch(Y.device)
+
+
+def mult_(Y: torch.Tensor, As: Sequence[RefinementMatrix], B: torch.Tensor, dims_refinement: Sequence[int]) -> None:
+    """``mult!(Y, As, B, dims_refinement)`` (K5) -- src/refinement_matrix.jl:421-445: left-multiply ``B`` by
+    every refinement matrix along its (1-based) dimension, into ``Y``."""
+    validate_mult_input(tuple(Y.shape), As, tuple(B.shape), dims_refinement)
+    _refmat_call("sg_refmat_mul_", Y, B, Y, B, As, dims_refinement)
+
+
+def mult_adjoint_(B: torch.Tensor, As: Sequence[RefinementMatrix], Y: torch.Tensor,
+                  dims_refinement: Sequence[int]) -> None:
+    """``mult_adjoint!(B, As, Y, dims_refinement)`` (K6) -- src/adjoint.jl:127-152 (B is overwritten)."""
+    validate_mult_input(tuple(Y.shape), As, tuple(B.shape), dims_refinement)
+    _refmat_call("sg_refmat_mul_adjoint_", B, Y, Y, B, As, dims_refinement)

@@ -1,0 +1,114 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, host-side logic
+(validation messages, ranges, slab partition), and loud failure without a device."""
+import ctypes as C
+import logging
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as entry
+
+
+@pytest.fixture(scope="module")
+def S():
+    return entry.load_package()
+
+
+def test_library_exports_every_declared_symbol(S):
+    lib = S._lib.lib()
+    names = S._lib.declared_symbols()
+    assert len(names) >= 38
+    for fam in ("sg_evaluate_", "sg_evaluate_adjoint_", "sg_basis_tables_", "sg_span_indices_", "sg_refmat_mul_",
+                "sg_refmat_mul_adjoint_", "sg_scatter_active_", "sg_gather_zero_active_", "sg_allreduce_sum_"):
+        assert fam + "f32" in names and fam + "f64" in names
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.sg_version() == 100
+    assert lib.sg_status_string(0) == b"SG_OK"
+    assert lib.sg_status_string(-2) == b"SG_ERR_UNSUPPORTED"
+
+
+def test_argument_validation_needs_no_device(S):
+    """Argument errors are reported before any CUDA call (no compute without a GPU)."""
+    lib = S._lib.lib()
+    assert lib.sg_span_indices_f64(None, None, C.c_int64(0), None, C.c_int64(0), C.c_int(0), None) == -1
+    n = (C.c_int64 * 1)(4)
+    assert lib.sg_evaluate_f32(None, C.c_int(1), n, n, C.c_int(1), None, None, None, None, None, None, None, None) == -1
+    assert lib.sg_evaluate_adjoint_workspace_bytes(C.c_int(0), None, None, C.c_int(1), None, C.c_int(4), C.c_int(0)) == 0
+    ns, nc, deg = (C.c_int64 * 2)(4096, 4096), (C.c_int64 * 2)(64, 64), (C.c_int * 2)(3, 3)
+    lib.sg_evaluate_adjoint_workspace_bytes.restype = C.c_size_t
+    small = lib.sg_evaluate_adjoint_workspace_bytes(C.c_int(2), ns, nc, C.c_int(3), deg, C.c_int(4), C.c_int(0))
+    big = lib.sg_evaluate_adjoint_workspace_bytes(C.c_int(2), ns, nc, C.c_int(3), deg, C.c_int(4), C.c_int(1))
+    assert 0 < small and big >= small + 4096 * 4096 * 4
+
+
+def test_no_cpu_fallback(S):
+    """Without a CUDA device the product path must fail loudly, never fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        S.SplineDimension(5, 2, 10)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        S.rmeye(4)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under splinegrids.jl_b200/ may reference it."""
+    import re
+    for p in entry.PKG_DIR.rglob("*"):
+        if p.suffix in (".py", ".cu", ".cuh", ".h", ".jl") and p.is_file():
+            text = p.read_text()
+            assert not re.search(r"\b(from|import)\s+oracle\b|oracle_np|oracle_c|liboracle", text), p
+
+
+def test_knot_vector_validation_messages(S):
+    """test/test_knot_vector.jl:11-24: raised before any device work."""
+    with pytest.raises(AssertionError, match="knot_values and multiplicities must be of the same length."):
+        S.KnotVector(np.arange(1, 6), np.arange(1, 4))
+    with pytest.raises(AssertionError, match="knot_values must be sorted."):
+        S.KnotVector(np.array([3, 2, 1]), np.arange(1, 4))
+    with pytest.raises(AssertionError, match="knot_values must be unique."):
+        S.KnotVector(np.array([1, 1, 2]), np.arange(1, 4))
+
+
+def test_julia_range_is_correctly_rounded(S):
+    from importlib import import_module
+    kvmod = import_module("splinegrids_jl_b200.knot_vector")
+    r = kvmod.julia_range(0, 1, 4, np.float64)
+    assert r.tolist() == [0.0, 1 / 3, 2 / 3, 1.0]
+    r32 = kvmod.julia_range(0, 1, 7, np.float32)
+    assert r32[3] == np.float32(0.5) and r32.dtype == np.float32
+    assert kvmod.julia_range(5.0, 7.0, 3, np.float64).tolist() == [5.0, 6.0, 7.0]
+
+
+def test_derivative_validation_host_side(S, caplog):
+    from importlib import import_module
+    val = import_module("splinegrids_jl_b200.validation")
+
+    class FakeDim:
+        def __init__(self, mdo):
+            self.max_derivative_order = mdo
+
+    with caplog.at_level(logging.ERROR, logger="splinegrids_b200"):
+        with pytest.raises(val.SplineGridsError, match=r"Invalid derivative order\(s\) supplied"):
+            val.validate_partial_derivatives((FakeDim(1), FakeDim(1)), (2, 3))
+    assert [r.getMessage() for r in caplog.records] == [
+        "The maximum derivative order available for spline dimension 1 is 1, got 2.",
+        "The maximum derivative order available for spline dimension 2 is 1, got 3."]
+    val.validate_partial_derivatives((FakeDim(1), FakeDim(0)), (1, 0))
+    with pytest.raises(val.SplineGridsError, match="Computing derivatives of NURBS is currently not supported."):
+        val.validate_partial_derivatives((FakeDim(1),), (1,), is_nurbs=True)
+
+
+def test_slab_bounds_partition(S):
+    for n in (1, 7, 64, 512, 8192, 1000):
+        for ws in (1, 2, 3, 4, 8):
+            if n < ws:
+                continue
+            b = [S.slab_bounds(n, ws, r) for r in range(ws)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[r][1] == b[r + 1][0] for r in range(ws - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+    assert S.slab_bounds(512, 8, 3) == (192, 256)

@@ -1,0 +1,536 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs, the
+reference's golden fixtures, and the reference's own test assertions re-stated for the package API.
+
+Tolerances (BASELINE.json north_star): bit-exact for span / sample indices, <= 1e-12 relative for
+Float64, <= 1e-5 relative for Float32 (norm-wise, like the reference's `≈`).
+"""
+import logging
+
+import numpy as np
+import pytest
+from helpers import TOL, julia_isapprox, load_g1, load_g2, max_rel_err, rel_err
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def S():
+    from gpu_helpers import sg
+    return sg()
+
+
+def _tol(ft):
+    return 1e-5 if ft == "Float32" else 1e-12
+
+
+# ---------------------------------------------------------------------------------------------
+# K1 / K2 / K9 / K10: per-dimension tables
+# ---------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("ft", ["Float32", "Float64"])
+@pytest.mark.parametrize("distribution", ["equispaced", "random"])
+def test_basis_tables_bit_exact_all_degrees(S, ft, distribution):
+    """test/test_spline_dimension.jl:10-29 shapes (25 basis functions, 500 samples, degree 0..5) plus degrees
+    up to 9; indices AND tables must be bit-identical to the oracle."""
+    from gpu_helpers import O, OC, oracle_dim
+    rng = np.random.default_rng(3)
+    for degree in range(0, 10):
+        for mdo in sorted({0, min(1, degree), min(2, degree), degree}):
+            sd = S.SplineDimension(25, degree, 500, float_type=ft, max_derivative_order=mdo,
+                                   distribution=distribution, rng=rng)
+            tab, idx = oracle_dim(sd, OC)
+            assert np.array_equal(S.to_numpy(sd.sample_indices), idx), (degree, mdo)
+            got = S.to_numpy(sd.eval)
+            assert got.shape == (500, degree + 1, mdo + 1)
+            assert np.array_equal(got, tab), (degree, mdo, np.abs(got - tab).max())
+            B = got[:, :, 0]
+            assert np.all(B >= 0)
+            assert np.allclose(B.sum(axis=1), 1, rtol=np.sqrt(np.finfo(B.dtype).eps))
+        # the numpy oracle agrees too (same operation order)
+        tab_np, idx_np = oracle_dim(sd, O)
+        assert np.array_equal(idx_np, idx) and np.array_equal(tab_np, tab)
+
+
+def test_knot_vector_expand_and_values(S):
+    """test/test_knot_vector.jl:26-41 (G10) through K9 on the device."""
+    kv = S.KnotVector.clamped(5, 2)
+    assert julia_isapprox(S.to_numpy(kv.knot_values), np.array([0, 1 / 3, 2 / 3, 1], dtype=np.float32))
+    assert S.to_numpy(kv.multiplicities).tolist() == [3, 1, 1, 3]
+    assert julia_isapprox(S.to_numpy(kv.knots_all), np.array([0, 0, 0, 1 / 3, 2 / 3, 1, 1, 1], dtype=np.float32))
+    kv2 = S.KnotVector.clamped(5, 2, extent=(5.0, 7.0))
+    assert julia_isapprox(S.to_numpy(kv2.knots_all), 2 * S.to_numpy(kv.knots_all) + 5)
+    S.KnotVector.clamped(10, 3, extent=(4, 8), distribution="random")
+    with pytest.raises(AssertionError):
+        S.KnotVector.clamped(5, 10)
+
+
+def test_span_indices_edge_cases(S):
+    """Repeated interior knots, samples on knots, out-of-range and NaN samples: bit-exact vs the literal scan."""
+    from gpu_helpers import O
+    for npdt, ft in ((np.float32, "Float32"), (np.float64, "Float64")):
+        kvals = np.array([0, 0.25, 0.5, 0.75, 1.0], dtype=npdt)
+        kv = S.KnotVector(kvals, np.array([3, 2, 1, 2, 3], dtype=np.int32))
+        sp = np.array([-1.0, 0.0, 0.1, 0.25, np.nextafter(npdt(0.25), npdt(0)), 0.5, 0.75, 0.9999, 1.0, 2.0, np.nan],
+                      dtype=npdt)
+        n_basis = int(kv.knots_all.numel()) - 3
+        sd = S.SplineDimension.from_fields(2, 0, kv, S.to_device(sp), torch.zeros(len(sp), dtype=torch.int32, device="cuda"),
+                                           S.jl_zeros((len(sp), 3, 1), kv.dtype, kv.device))
+        S.set_sample_indices_(sd)
+        ref = O.span_indices(sp, S.to_numpy(kv.knots_all), 2)
+        assert np.array_equal(S.to_numpy(sd.sample_indices), ref)
+        assert ref[-1] == n_basis and ref[-2] == n_basis          # NaN and t > t_max -> last span
+
+
+def test_derivative_tables_vs_finite_differences(S):
+    """test/test_spline_dimension.jl:31-66 (G6) through K2 + K10 (decompress)."""
+    sd = S.SplineDimension(10, 3, 5000, max_derivative_order=2, float_type="Float64")
+    sp = S.to_numpy(sd.sample_points)
+    dt = np.diff(sp)
+    data, d1, d2 = (S.to_numpy(S.decompress(sd, derivative_order=k)) for k in range(3))
+    fd = np.diff(data, axis=0) / dt[:, None]
+    fd2 = np.diff(fd, axis=0) / dt[1:, None]
+    assert julia_isapprox(d1[:-1], fd, rtol=1e-2)
+    assert julia_isapprox(d2[2:], fd2, rtol=1e-2)
+
+
+# ---------------------------------------------------------------------------------------------
+# K3: evaluate!
+# ---------------------------------------------------------------------------------------------
+
+
+def test_g4_ones_in_ones_out(S):
+    """test/test_spline_grid.jl:11-27: degree 1..n_basis-1 up to 9, including the Bezier case."""
+    for n_basis in range(2, 11):
+        for degree in range(1, n_basis):
+            grid = S.SplineGrid(S.SplineDimension(n_basis, degree, 100), 1)
+            grid.control_points.fill_(1)
+            S.evaluate_(grid)
+            assert np.allclose(S.to_numpy(grid.eval), 1, rtol=np.sqrt(np.finfo(np.float32).eps)), (n_basis, degree)
+
+
+def test_g1_golden_grid(S):
+    """test/test_spline_grid.jl:29-53: the reference's golden vector, end to end (K1+K2+K3)."""
+    from gpu_helpers import oracle_evaluate
+    g, cp, ev = load_g1()
+    dims = tuple(S.SplineDimension(c, p, n) for c, p, n in zip(g["n_control_points"], g["degree"], g["n_sample_points"]))
+    assert S.to_numpy(dims[0].sample_indices).tolist() == [4, 4, 4, 5, 5, 5, 5]
+    assert S.to_numpy(dims[1].sample_indices).tolist() == [3, 3, 4, 4, 5, 5, 6, 6, 6]
+    grid = S.SplineGrid(dims, g["Nout"])
+    S.copyto_(grid.control_points, cp.astype(np.float32))
+    S.evaluate_(grid)
+    got = S.to_numpy(grid.eval)
+    assert got.shape == (7, 9, 2)
+    assert julia_isapprox(got, ev.astype(np.float32))             # the reference's own assertion
+    assert rel_err(got, ev) < 2e-7
+    assert rel_err(got, oracle_evaluate(grid, cp.astype(np.float32))) < 1e-6
+
+
+def test_g3_nurbs_circle(S):
+    """test/test_nurbs_grid.jl:25-52."""
+    kv = S.KnotVector(np.array([0, np.pi / 2, np.pi, 3 * np.pi / 2, 2 * np.pi], dtype=np.float32),
+                      np.array([3, 2, 2, 2, 3], dtype=np.int32))
+    sd = S.SplineDimension(9, 2, 500, knot_vector=kv)
+    grid = S.NURBSGrid(sd, 2)
+    grid.weights[1::2] = 1 / np.sqrt(2)
+    S.copyto_(grid.control_points,
+              np.array([[1, 0], [1, 1], [0, 1], [-1, 1], [-1, 0], [-1, -1], [0, -1], [1, -1], [1, 0]], dtype=np.float32))
+    S.evaluate_(grid)
+    pts = S.to_numpy(grid.eval).astype(np.float64)
+    assert np.all(np.abs(pts[:, 0] ** 2 + pts[:, 1] ** 2 - 1) <= np.sqrt(np.finfo(np.float32).eps))
+    assert len({tuple(r) for r in S.to_numpy(grid.eval)[1:]}) == 499
+
+
+CASES = [
+    # n_cp, degree, n_samples, nout, float type, mdo, nurbs
+    ((7,), (3,), (41,), 1, "Float64", 0, False),
+    ((9,), (5,), (33,), 3, "Float32", 0, True),
+    ((10, 10, 5), (2, 3, 2), (50, 50, 25), 4, "Float64", 0, False),       # BASELINE config C1
+    ((5, 6), (3, 2), (7, 9), 2, "Float32", 1, False),
+    ((12, 10), (3, 4), (26, 73), 3, "Float64", 2, False),
+    ((12, 10), (3, 4), (26, 73), 3, "Float64", 0, True),
+    ((6, 6), (2, 2), (50, 50), 3, "Float32", 0, False),
+    ((5, 8, 6), (4, 2, 3), (15, 20, 25), 2, "Float32", 0, False),
+    ((4, 5, 4, 3), (1, 2, 3, 2), (6, 7, 5, 4), 5, "Float64", 0, False),   # Nin = 4, Nout > chunk
+    ((10,), (9,), (100,), 1, "Float32", 0, False),                        # Bezier, degree 9
+    ((4, 4), (3, 3), (9, 300), 1, "Float64", 1, False),                   # single span per dimension
+    ((16, 16), (3, 3), (128, 96), 3, "Float32", 1, False),
+    ((16, 16, 16), (3, 3, 3), (40, 36, 44), 1, "Float64", 0, False),
+    ((16, 16), (3, 3), (128, 96), 3, "Float32", 0, True),
+    ((20, 3), (2, 2), (3, 50), 2, "Float64", 0, False),                   # fewer samples than spans
+]
+
+
+@pytest.mark.parametrize("policy", [1, 0, 2])
+@pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}-{c[1]}-{c[4]}{'-nurbs' if c[6] else ''}" for c in CASES])
+def test_evaluate_and_adjoint_vs_oracle(S, case, policy):
+    """K3 and K4 against the C oracle (the reference's algorithm) for every kernel policy
+    (1 = generic kernels, 0 = automatic dispatch, 2 = tiled fast paths forced)."""
+    from gpu_helpers import make_grid, oracle_adjoint, oracle_evaluate
+    n_cp, deg, n_s, nout, ft, mdo, nurbs = case
+    grid, cp, w, rng = make_grid(n_cp, deg, n_s, nout, ft, mdo=mdo, nurbs=nurbs, seed=11)
+    tol = _tol(ft)
+    S.set_kernel_policy(policy)
+    try:
+        ders = [(0,) * len(n_cp)]
+        if mdo and not nurbs:
+            ders += [tuple(min(mdo, p) if d == k else 0 for d, p in enumerate(deg)) for k in range(len(n_cp))]
+            ders += [tuple(min(mdo, p) for p in deg)]
+        for der in ders:
+            S.evaluate_(grid, derivative_order=der)
+            ref = oracle_evaluate(grid, cp, der, w)
+            assert rel_err(S.to_numpy(grid.eval), ref) <= tol, (der, S.last_variant())
+            assert max_rel_err(S.to_numpy(grid.eval), ref) <= 10 * tol, (der, S.last_variant())
+            e = np.asfortranarray(rng.random(ref.shape).astype(ref.dtype))
+            g = torch.full_like(grid.control_points.obtain(), 7.0)    # must be overwritten (zero fill, adjoint.jl:61)
+            S.evaluate_adjoint_(grid, derivative_order=der, eval=S.to_device(e), control_points=g, allow_nurbs=nurbs)
+            gref = oracle_adjoint(grid, e, der, w)
+            assert rel_err(S.to_numpy(g), gref) <= tol, (der, S.last_variant())
+            assert max_rel_err(S.to_numpy(g), gref) <= 10 * tol, (der, S.last_variant())
+    finally:
+        S.set_kernel_policy(0)
+
+
+def test_evaluate_with_raw_and_reshaped_arrays(S):
+    """control_points / eval kwargs accept raw arrays and reshaped flat vectors (test/test_EnzymeExt.jl:24-28,
+    ext/SplineGridsLinearMapsExt.jl:26-30)."""
+    from gpu_helpers import make_grid, oracle_evaluate
+    grid, cp, _, rng = make_grid((8, 9), (3, 2), (30, 40), 2, "Float64")
+    flat_cp = S.to_device(cp.ravel(order="F"))
+    flat_ev = torch.empty(30 * 40 * 2, dtype=torch.float64, device="cuda")
+    S.evaluate_(grid, control_points=S.reshape_colmajor(flat_cp, (8, 9, 2)), eval=S.reshape_colmajor(flat_ev, (30, 40, 2)))
+    ref = oracle_evaluate(grid, cp)
+    assert rel_err(flat_ev.cpu().numpy(), ref.ravel(order="F")) <= 1e-12
+    with pytest.raises(AssertionError):
+        S.evaluate_(grid, eval=torch.empty(30, 41, 2, dtype=torch.float64, device="cuda"))
+
+
+def test_nonmonotone_sample_points_use_scatter_path(S):
+    """User-built SplineDimension with UNSORTED sample points (struct constructor, src/spline_dimension.jl:40-65):
+    forward and adjoint must still match the oracle (adjoint falls back to the atomic scatter on device)."""
+    from gpu_helpers import O
+    rng = np.random.default_rng(5)
+    dims, odims = [], []
+    for c, p, n in zip((9, 7), (3, 2), (300, 280)):
+        kv = S.KnotVector.clamped(c, p, float_type_="Float64")
+        sp = rng.random(n)                                           # unsorted
+        sd = S.SplineDimension.from_fields(p, 0, kv, S.to_device(sp), torch.zeros(n, dtype=torch.int32, device="cuda"),
+                                           S.jl_zeros((n, p + 1, 1), torch.float64, "cuda"))
+        S.build_(sd)
+        idx = O.span_indices(sp, S.to_numpy(kv.knots_all), p)
+        assert np.array_equal(idx, S.to_numpy(sd.sample_indices))
+        odims.append((O.basis_tables(S.to_numpy(kv.knots_all), sp, idx, p, 0), idx))
+        dims.append(sd)
+    grid = S.SplineGrid(tuple(dims), 3)
+    cp = np.asfortranarray(rng.random((9, 7, 3)))
+    S.copyto_(grid.control_points, cp)
+    S.evaluate_(grid)
+    ref = O.evaluate([t for t, _ in odims], [i for _, i in odims], [3, 2], [0, 0], cp)
+    assert rel_err(S.to_numpy(grid.eval), ref) <= 1e-12
+    e = np.asfortranarray(rng.random(ref.shape))
+    S.evaluate_adjoint_(grid, eval=S.to_device(e))
+    gref = O.evaluate_adjoint([t for t, _ in odims], [i for _, i in odims], [3, 2], [0, 0], e, (9, 7, 3))
+    assert rel_err(S.to_numpy(grid.control_points.obtain()), gref) <= 1e-12
+
+
+def test_nurbs_adjoint_is_transpose_of_forward(S):
+    """The NURBS adjoint has no reference behaviour (src/adjoint.jl:52-57): pin it as the exact transpose of our
+    own forward map via <R p, e> = <p, R' e>, and as the plain adjoint when all weights are 1."""
+    from gpu_helpers import make_grid, oracle_adjoint
+    grid, cp, w, rng = make_grid((11, 9), (3, 2), (60, 50), 2, "Float64", nurbs=True, seed=2)
+    e = np.asfortranarray(rng.random((60, 50, 2)))
+    S.evaluate_(grid)
+    fwd = S.to_numpy(grid.eval)
+    g = torch.zeros_like(grid.control_points.obtain())
+    S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g, allow_nurbs=True)
+    lhs, rhs = float((fwd * e).sum()), float((cp * S.to_numpy(g)).sum())
+    assert abs(lhs - rhs) <= 1e-12 * abs(lhs)
+    with pytest.raises(TypeError):
+        S.evaluate_adjoint_(grid, eval=S.to_device(e))              # the reference has no such method
+    grid.weights.fill_(1)
+    S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g, allow_nurbs=True)
+    assert rel_err(S.to_numpy(g), oracle_adjoint(grid, e)) <= 1e-12
+
+
+def test_derivative_order_validation_messages(S, caplog):
+    """test/test_spline_grid.jl:55-83 and test/test_nurbs_grid.jl:11-23."""
+    dims = tuple(S.SplineDimension(c, p, n, max_derivative_order=1) for c, p, n in zip((5, 6), (3, 2), (7, 9)))
+    grid = S.SplineGrid(dims, 2)
+    with caplog.at_level(logging.ERROR, logger="splinegrids_b200"):
+        with pytest.raises(S.SplineGridsError, match=r"Invalid derivative order\(s\) supplied. If you want to evaluate "
+                                                     r"\(higher order\) derivatives, specify this at construction as "
+                                                     r"SplineDimension\(...; max_derivative_order\)."):
+            S.evaluate_(grid, derivative_order=(2, 1))
+    assert len(caplog.records) == 1
+    assert caplog.records[0].getMessage() == "The maximum derivative order available for spline dimension 1 is 1, got 2."
+    nurbs = S.NURBSGrid(S.SplineDimension(4, 2, 100, max_derivative_order=1), 1)
+    with pytest.raises(S.SplineGridsError, match="Computing derivatives of NURBS is currently not supported."):
+        S.evaluate_(nurbs, derivative_order=(1,))
+
+
+# ---------------------------------------------------------------------------------------------
+# K5-K8: refinement matrices and the hierarchy
+# ---------------------------------------------------------------------------------------------
+
+
+def test_refinement_matrix_unit_tests(S):
+    """test/test_refinement_matrix.jl:16-75."""
+    M = S.rmeye(100)
+    assert M[25, 25] == 1 and M[25, 26] == 0
+    with pytest.raises(S.SplineGridsError, match=r"Index \(101, 1\) out of bounds for refinement matrix of size \(100, 100\)."):
+        M[101, 1]
+    M2 = M @ M
+    assert M2 == M and M2.shape == (100, 100) and len(M2) == 100 ** 2
+    rng = np.random.default_rng(1)
+    A, B = S.refinement_matrix_from_dense(np.diag(rng.random(100))), S.refinement_matrix_from_dense(np.diag(rng.random(100)))
+    assert np.array_equal((A @ B).nzval_host, A.nzval_host * B.nzval_host)
+
+    def brand(m, n, lo, up):
+        a = rng.random((m, n))
+        i, j = np.indices((m, n))
+        a[(i - j > lo) | (j - i > up)] = 0
+        return a
+
+    Ad, Bd = brand(100, 100, 4, 3), brand(100, 200, 3, 5)
+    Cm = S.refinement_matrix_from_dense(Ad) @ S.refinement_matrix_from_dense(Bd)
+    assert julia_isapprox(Cm.collect(), Ad @ Bd)
+    Mz = np.zeros((2, 50))
+    Mz[0, :20] = 1
+    Mz[1, 38:] = 1
+    with pytest.raises(S.SplineGridsError, match=r"Invalid rows: \[2\]\."):
+        S.refinement_matrix_from_dense(Mz)
+    Mz = np.zeros((3, 50))
+    Mz[0, :25] = 1
+    Mz[2, 25:] = 1
+    with pytest.raises(S.SplineGridsError, match=r"Invalid rows: \[2, 3\]\."):
+        S.refinement_matrix_from_dense(Mz)
+
+
+@pytest.mark.parametrize("ft", ["Float32", "Float64"])
+def test_mult_and_mult_adjoint_vs_oracle(S, ft):
+    """K5 / K6 with random banded matrices on 1, 2 and 3 refined dimensions of a 4-d array."""
+    from gpu_helpers import O, OC
+    rng = np.random.default_rng(9)
+    npdt = np.float32 if ft == "Float32" else np.float64
+
+    def banded(m, n):
+        a = np.zeros((m, n), dtype=npdt)
+        for i in range(m):
+            c = int(round(i * (n - 1) / max(m - 1, 1)))
+            lo, hi = max(0, c - rng.integers(0, 3)), min(n, c + 1 + rng.integers(0, 3))
+            a[i, lo:hi] = rng.random(hi - lo) + 0.1
+        a[0, 0] = 1
+        return a
+
+    sizeB = (6, 7, 5, 3)
+    B = np.asfortranarray(rng.random(sizeB).astype(npdt))
+    for dims_ref, ms in (((2,), (11,)), ((1, 3), (10, 9)), ((3, 1, 2), (8, 9, 12))):
+        As_d = [banded(m, sizeB[d - 1]) for d, m in zip(dims_ref, ms)]
+        As = [S.refinement_matrix_from_dense(a) for a in As_d]
+        As_o = [O.refmat_from_dense(a) for a in As_d]
+        sizeY = list(sizeB)
+        for d, m in zip(dims_ref, ms):
+            sizeY[d - 1] = m
+        Y = S.jl_zeros(sizeY, As[0].dtype, "cuda")
+        S.mult_(Y, As, S.to_device(B), dims_ref)
+        Yo = np.zeros(sizeY, dtype=npdt, order="F")
+        OC.mult(Yo, As_o, B, list(dims_ref))
+        assert rel_err(S.to_numpy(Y), Yo) <= _tol(ft)
+        Yin = np.asfortranarray(rng.random(sizeY).astype(npdt))
+        Bout = S.jl_empty(sizeB, As[0].dtype, "cuda")
+        Bout.fill_(3.0)                                              # must be overwritten (B .= 0, adjoint.jl:135)
+        S.mult_adjoint_(Bout, As, S.to_device(Yin), dims_ref)
+        Bo = np.zeros(sizeB, dtype=npdt, order="F")
+        OC.mult_adjoint(Bo, As_o, Yin, list(dims_ref))
+        assert rel_err(S.to_numpy(Bout), Bo) <= _tol(ft)
+    with pytest.raises(S.SplineGridsError, match="Size of refinement matrix does not match `B` and `Y` along refinement dimension 2."):
+        S.mult_(S.jl_zeros((6, 12, 5, 3), As[0].dtype, "cuda"), [S.rmeye(7, float_type_=ft)], S.to_device(B), (2,))
+
+
+def _g7_grid(S):
+    rng = np.random.default_rng(1)
+    dims = tuple(S.SplineDimension(c, p, n, distribution="random", rng=rng)
+                 for c, p, n in zip((5, 8, 6), (4, 2, 3), (15, 20, 25)))
+    grid = S.SplineGrid(dims, 2)
+    S.copyto_(grid.control_points, rng.random((5, 8, 6, 2)).astype(np.float32))
+    S.evaluate_(grid)
+    return grid
+
+
+def test_g7_knot_insertion_and_refine_preserve_geometry(S):
+    """test/test_refinement.jl:29-58."""
+    grid0 = _g7_grid(S)
+    ev0 = S.to_numpy(grid0.eval).copy()
+    grid = grid0
+    for dr in (1, 2, 3):
+        grid, R = S.insert_knot(grid, dr, 0.25)
+        grid = grid.replace(eval=torch.zeros_like(grid0.eval))
+        S.evaluate_(grid)
+        assert julia_isapprox(S.to_numpy(grid.eval), ev0)
+        shp = grid.control_points.shape
+        assert R.shape == (shp[dr - 1], shp[dr - 1] - 1)
+    grid = grid0
+    old = grid0.control_points.shape
+    for dr in (1, 2, 3):
+        grid, R = S.refine(grid, dr)
+        grid = grid.replace(eval=torch.zeros_like(grid0.eval))
+        S.evaluate_(grid)
+        assert julia_isapprox(S.to_numpy(grid.eval), ev0)
+        assert R.shape == (grid.control_points.shape[dr - 1], old[dr - 1])
+
+
+def test_g8_local_refinement_counts(S):
+    """test/test_local_refinement.jl:11-46 + the second level of docs/src/theory_local_refinement.md:19-63."""
+    dims = tuple(S.SplineDimension(6, 2, 500) for _ in range(2))
+    grid = S.SplineGrid(dims, 3)
+    assert S.get_n_control_points(grid) == 36
+    assert S.evaluate_(grid.control_points) is None
+    grid = S.add_default_local_refinement(grid)
+    cps = grid.control_points
+    assert isinstance(cps, S.LocallyRefinedControlPoints)
+    assert "LocallyRefinedControlPoints for final grid of size (10, 10) in R^3 (torch.float32). Local refinements:" in repr(cps)
+    assert S.get_n_control_points(grid) == 36
+    before = S.to_numpy(S.obtain(cps)).copy()
+    S.activate_local_control_point_range_(grid, range(1, 5), range(1, 7))
+    S.activate_local_control_point_range_(grid, range(1, 7), range(1, 3))
+    S.activate_local_control_point_range_(grid, range(9, 11), range(7, 11))
+    S.deactivate_overwritten_control_points_(grid.control_points)
+    S.evaluate_(grid.control_points)
+    assert S.get_n_control_points(grid) == 63
+    assert julia_isapprox(S.to_numpy(S.obtain(cps)), before)
+    grid = S.add_default_local_refinement(grid)
+    assert S.obtain(grid.control_points).shape == (18, 18, 3)
+    S.activate_local_control_point_range_(grid, range(5, 13), range(1, 5))
+    S.activate_local_control_point_range_(grid, range(7, 9), range(5, 7))
+    S.deactivate_overwritten_control_points_(grid.control_points)
+    fine = S.to_numpy(S.obtain(grid.control_points)).copy()
+    S.evaluate_(grid.control_points)
+    assert julia_isapprox(S.to_numpy(S.obtain(grid.control_points)), fine)
+    # same hierarchy through the oracle: identical active sets, finest control points and evaluation
+    from gpu_helpers import O, oracle_dim
+    odims = [O.make_dimension(6, 2, 500) for _ in range(2)]
+    odims, olr = O.add_default_local_refinement(odims, O.unit_cp_grid((6, 6, 3), np.float32))
+    O.activate_local_control_point_range(olr, (1, 4), (1, 6))
+    O.activate_local_control_point_range(olr, (1, 6), (1, 2))
+    O.activate_local_control_point_range(olr, (9, 10), (7, 10))
+    O.deactivate_overwritten_control_points(olr)
+    odims, olr = O.add_default_local_refinement(odims, olr)
+    O.activate_local_control_point_range(olr, (5, 12), (1, 4))
+    O.activate_local_control_point_range(olr, (7, 8), (5, 6))
+    O.deactivate_overwritten_control_points(olr)
+    for lr_g, lr_o in zip(grid.control_points.local_refinements, olr.local_refinements):
+        assert np.array_equal(S.to_numpy(lr_g.refinement_indices).reshape(-1, 2), lr_o.refinement_indices)
+    rng = np.random.default_rng(42)
+    vals = rng.random((S.get_n_control_points(grid), 3)).astype(np.float32)
+    S.copyto_(grid.control_points, vals)
+    S.evaluate_(grid.control_points)
+    olr.set_values(vals)
+    O.lrcp_evaluate(olr, fast=False)
+    assert rel_err(S.to_numpy(S.obtain(grid.control_points)), olr.control_points_refined[-1]) <= 1e-5
+    S.evaluate_(grid)
+    tabs = [oracle_dim(sd, O) for sd in grid.spline_dimensions]
+    ref = O.evaluate([t for t, _ in tabs], [i for _, i in tabs], [2, 2], [0, 0],
+                     np.asfortranarray(olr.control_points_refined[-1]))
+    assert rel_err(S.to_numpy(grid.eval), ref) <= 1e-5
+
+
+def test_g2_error_informed_refinement_golden_indices(S):
+    """test/test_local_refinement.jl:48-67: exact 18x2 Int32 index set through the device adjoint."""
+    _, expected = load_g2()
+    dims = tuple(S.SplineDimension(6, 2, 50) for _ in range(2))
+    grid = S.add_default_local_refinement(S.SplineGrid(dims, 3))
+    err = torch.zeros_like(grid.eval)
+    err[19:40, 9:30, 1] = 1
+    for policy in (1, 0, 2):
+        g = S.add_default_local_refinement(S.SplineGrid(dims, 3))
+        S.set_kernel_policy(policy)
+        try:
+            S.error_informed_local_refinement_(g, err)
+        finally:
+            S.set_kernel_policy(0)
+        got = S.to_numpy(g.control_points.local_refinements[-1].refinement_indices)
+        assert got.dtype == np.int32 and np.array_equal(got, expected)
+
+
+def _lsqr(A, b):
+    """scipy lsqr over the device linear map (host vectors in, device kernels inside)."""
+    from scipy.sparse.linalg import LinearOperator, lsqr
+    import gpu_helpers
+    S_ = gpu_helpers.sg()
+
+    def mv(x):
+        return A.matvec(S_.to_device(np.asarray(x, dtype=np.float64))).cpu().numpy()
+
+    def rmv(y):
+        return A.rmatvec(S_.to_device(np.asarray(y, dtype=np.float64))).cpu().numpy()
+
+    return lsqr(LinearOperator(A.shape, matvec=mv, rmatvec=rmv, dtype=np.float64), b, atol=1e-12, btol=1e-12,
+                iter_lim=2000)[0]
+
+
+def test_g9_least_squares_fitting(S):
+    """test/test_LinearMapsExt.jl:14-33."""
+    rng = np.random.default_rng(1)
+    dims = tuple(S.SplineDimension(c, p, n, float_type="Float64") for c, p, n in zip((12, 10), (3, 4), (26, 73)))
+    grid = S.SplineGrid(dims, 3)
+    cp = rng.random((12, 10, 3))
+    S.copyto_(grid.control_points, cp)
+    S.evaluate_(grid)
+    A = S.SplineGridLinearMap(grid)
+    fit = _lsqr(A, S.to_numpy(grid.eval).ravel(order="F").copy())
+    assert np.allclose(fit, cp.ravel(order="F"), rtol=1e-5)
+
+
+def test_g9_locally_refined_least_squares_fitting(S):
+    """test/test_LinearMapsExt.jl:35-62 (K3-K8 mutually adjoint and consistent)."""
+    rng = np.random.default_rng(1)
+    dims = tuple(S.SplineDimension(c, p, n, float_type="Float64") for c, p, n in zip((12, 10), (3, 4), (26, 73)))
+    grid = S.add_default_local_refinement(S.SplineGrid(dims, 3))
+    S.activate_local_control_point_range_(grid, range(1, 5), range(1, 7))
+    S.activate_local_control_point_range_(grid, range(1, 7), range(1, 3))
+    S.activate_local_control_point_range_(grid, range(9, 11), range(7, 11))
+    S.deactivate_overwritten_control_points_(grid.control_points)
+    n_cp = S.get_n_control_points(grid)
+    vals = rng.random((n_cp, 3))
+    S.copyto_(grid.control_points, vals)
+    S.evaluate_(grid.control_points)
+    S.evaluate_(grid)
+    target = S.to_numpy(grid.eval).ravel(order="F").copy()
+    A = S.SplineGridLinearMap(grid)
+    x, y = rng.random(A.shape[1]), rng.random(A.shape[0])
+    lhs = float(A.matvec(S.to_device(x)).cpu().numpy() @ y)
+    rhs = float(x @ A.rmatvec(S.to_device(y)).cpu().numpy())
+    assert abs(lhs - rhs) <= 1e-12 * abs(lhs)
+    fit = _lsqr(A, target)
+    assert np.allclose(fit, vals.ravel(order="F"), rtol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# C ABI behaviour
+# ---------------------------------------------------------------------------------------------
+
+
+def test_c_abi_error_codes(S):
+    import ctypes as C
+    lib = S._lib.lib()
+    assert lib.sg_span_indices_f32(None, None, C.c_int64(4), None, C.c_int64(8), C.c_int(2), None) == -1
+    assert lib.sg_status_string(-1) == b"SG_ERR_INVALID_ARGUMENT"
+    t = torch.zeros(8, device="cuda")
+    idx = torch.zeros(8, dtype=torch.int32, device="cuda")
+    # degree above SG_MAX_DEGREE
+    assert lib.sg_basis_tables_f32(S._lib.ptr(t), S._lib.ptr(t), C.c_int64(40), S._lib.ptr(t), S._lib.ptr(idx),
+                                   C.c_int64(8), C.c_int(16), C.c_int(0), None) == -2
+    # misaligned / short workspace
+    grid = S.SplineGrid(tuple(S.SplineDimension(16, 3, 200) for _ in range(2)), 3)
+    from importlib import import_module
+    sgmod = import_module("splinegrids_jl_b200.spline_grid")
+    args = sgmod._grid_call_args(grid, (0, 0))
+    ws = torch.empty(64, dtype=torch.uint8, device="cuda")
+    rc = lib.sg_evaluate_adjoint_f32(S._lib.ptr(grid.control_points.obtain()), *args, S._lib.ptr(grid.eval), None,
+                                     S._lib.ptr(ws), C.c_size_t(64), None)
+    assert rc == -3
+    before = S.launch_count()
+    S.evaluate_(grid)
+    assert S.launch_count() == before + 1
