@@ -316,12 +316,15 @@ def test_mult_and_mult_adjoint_vs_oracle(S, ft):
     npdt = np.float32 if ft == "Float32" else np.float64
 
     def banded(m, n):
+        """Random valid refinement-matrix structure (m >= n): monotone, touching row windows."""
         a = np.zeros((m, n), dtype=npdt)
+        lo_prev, hi_prev = 0, 1
         for i in range(m):
             c = int(round(i * (n - 1) / max(m - 1, 1)))
-            lo, hi = max(0, c - rng.integers(0, 3)), min(n, c + 1 + rng.integers(0, 3))
+            lo = 0 if i == 0 else min(max(lo_prev, c - int(rng.integers(0, 3))), hi_prev)
+            hi = min(n, max(hi_prev, c + 1 + int(rng.integers(0, 3))))
             a[i, lo:hi] = rng.random(hi - lo) + 0.1
-        a[0, 0] = 1
+            lo_prev, hi_prev = lo, hi
         return a
 
     sizeB = (6, 7, 5, 3)
