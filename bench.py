@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Benchmark of the grid-evaluation hot path (BASELINE.json metric: evaluate!/adjoint sample-values/sec).
+
+Workload (config.workload): BASELINE config 3 -- 3-D cubic volume, 128^3 control points, 512^3 samples, Nout=1,
+Float64 (1.07 GB output, > L2).  One STEP = one `evaluate!` + one `evaluate_adjoint!` on that grid (what one
+iteration of the reference's LinearMap/lsqr fitting loop does, ext/SplineGridsLinearMapsExt.jl:16-48).
+With N GPUs the sample grid is sharded in slabs along its slowest axis (strong scaling: total work fixed),
+control points replicated, and the adjoint's per-GPU gradients are summed with an NCCL all-reduce.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (torchrun for N > 1)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores
+
+`value`   = sample-values/s, kernels only, inputs resident in HBM (CUDA events, max over ranks).
+`e2e`     = same metric through the public API with HOST buffers: pinned H2D of the inputs and D2H of the
+            results inside the timed region.
+`roofline`= dominant kernel's algorithmic bytes / its live CUDA-event duration vs MEASURED_PEAKS.json.
+The CPU arm is the C/OpenMP restatement of the reference's algorithm (oracle/): Julia is not installed in the
+image, so the reference package itself cannot run (DESIGN.md "Oracle").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOAD = dict(name="C3: 3-D cubic volume, control 128^3, samples 512^3, Nout=1, Float64",
+                n_cp=(128, 128, 128), degree=(3, 3, 3), n_samples=(512, 512, 512), nout=1, float_type="Float64")
+METRIC = "evaluate!+evaluate_adjoint! sample-values/sec"
+UNIT = "sample-values/s"
+
+
+def algorithmic_bytes(n_samples, n_cp, degree, nout, elem=8):
+    """output (or adjoint input) + control points + selected table slices + span indices."""
+    n, c = int(np.prod(n_samples)), int(np.prod(n_cp))
+    return n * nout * elem + c * nout * elem + sum(nd * ((p + 1) * elem + 4) for nd, p in zip(n_samples, degree))
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return json.loads(p.read_text()), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": float(np.max(power))}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (C/OpenMP restatement) on a bounded slab of the workload
+# --------------------------------------------------------------------------------------------
+
+
+def cpu_reference_setup(planes: int):
+    from oracle import oracle_c as OC
+    from oracle import oracle_np as O
+    w = WORKLOAD
+    npdt = np.float64
+    dims = []
+    for d, (c, p, n) in enumerate(zip(w["n_cp"], w["degree"], w["n_samples"])):
+        kv, mu, ka = O.clamped_knot_vector(c, p, npdt)
+        sp = O.default_sample_points(kv, n)
+        if d == len(w["n_cp"]) - 1:
+            sp = np.ascontiguousarray(sp[:planes])           # a slab of `planes` rows along the slowest axis
+        idx = OC.span_indices(sp, ka, p)
+        dims.append((OC.basis_tables(ka, sp, idx, p, 0), idx))
+    rng = np.random.default_rng(1)
+    cp = np.asfortranarray(rng.random(w["n_cp"] + (w["nout"],)))
+    n_s = w["n_samples"][:-1] + (planes,)
+    e_in = np.asfortranarray(np.random.default_rng(3).random(n_s + (w["nout"],)))
+    out = np.empty(n_s + (w["nout"],), dtype=npdt, order="F")
+    g = np.empty(w["n_cp"] + (w["nout"],), dtype=npdt, order="F")
+    tabs, idxs = [t for t, _ in dims], [i for _, i in dims]
+
+    def step():
+        OC.evaluate(tabs, idxs, w["degree"], [0, 0, 0], cp, None, out)
+        OC.evaluate_adjoint(tabs, idxs, w["degree"], [0, 0, 0], e_in, g.shape, None, g)
+
+    values = 2 * int(np.prod(n_s)) * w["nout"]
+    return step, values, OC.max_threads()
+
+
+def run_cpu_reference(steps: int, warmup: int, planes: int):
+    step, values, cores = cpu_reference_setup(planes)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return values / dt, dt, cores
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    planes = args.cpu_planes
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    value, dt, cores = run_cpu_reference(steps, warmup, planes)
+    sample = (f"slab of {planes}/512 planes of the C3 grid (512x512x{planes} samples, all 128^3 control points), "
+              f"evaluate!+adjoint, C/OpenMP restatement of the reference algorithm (Julia unavailable), {cores} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD["name"], "cpu_sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+
+
+def main_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as entry
+    S = entry.load_package()                       # fails loudly if libsplinegrids_b200.so is missing
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    if args.gpus != world and rank == 0:
+        print(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+
+    w = WORKLOAD
+    S.set_synchronous(False)                       # the benchmark synchronises once per timed region
+    gdims = tuple(S.SplineDimension(c, p, n, float_type=w["float_type"])
+                  for c, p, n in zip(w["n_cp"], w["degree"], w["n_samples"]))
+    sh = S.SlabShardedGrid(gdims, w["nout"], rank, world)
+    grid = sh.local
+    n_local = tuple(grid.eval.shape[:-1])
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1)
+    cp = grid.control_points.obtain()
+    cp.copy_(torch.rand(cp.shape, dtype=cp.dtype, device=dev, generator=gen))        # replicated (same seed)
+    gen.manual_seed(3 + rank)
+    e_in = torch.empty_like(grid.eval)
+    e_in.copy_(torch.rand(e_in.shape, dtype=e_in.dtype, device=dev, generator=gen))
+    grad = torch.zeros_like(cp)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        S.evaluate_(grid)
+        sh.evaluate_adjoint_(eval=e_in, control_points=grad)          # local adjoint + NCCL all-reduce (N > 1)
+
+    values_per_step = 2 * int(np.prod(w["n_samples"])) * w["nout"]      # whole job, both ops
+
+    # ---- kernel-only timing: K steps between two events, max over ranks ---------------------------
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    S.launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = S.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = values_per_step / (ms_step * 1e-3)
+
+    # ---- per-op and dominant-kernel timings (live CUDA events on the launch stream) ----------------
+    def time_fn(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fn()                                        # keep the queue busy so launch overhead is hidden
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    reps = max(3, min(args.steps, 10))
+    ms_fwd = time_fn(lambda: S.evaluate_(grid), reps)
+    var_fwd = S.last_variant()
+    ms_adj = time_fn(lambda: S.evaluate_adjoint_(grid, eval=e_in, control_points=grad), reps)
+    var_adj = S.last_variant()
+    peaks, peak_kind = load_peaks()
+    hbm = float(peaks["hbm_gbs"])
+    nb_local = algorithmic_bytes(n_local, w["n_cp"], w["degree"], w["nout"])
+    n_local_values = int(np.prod(n_local)) * w["nout"]
+    ops = {
+        "evaluate": {"ms": ms_fwd, "values_per_s": n_local_values / (ms_fwd * 1e-3), "variant": var_fwd,
+                     "achieved_GBs": nb_local / (ms_fwd * 1e-3) / 1e9, "frac_of_hbm_roofline": nb_local / (ms_fwd * 1e-3) / 1e9 / hbm},
+        "evaluate_adjoint": {"ms": ms_adj, "values_per_s": n_local_values / (ms_adj * 1e-3), "variant": var_adj,
+                             "achieved_GBs": nb_local / (ms_adj * 1e-3) / 1e9,
+                             "frac_of_hbm_roofline": nb_local / (ms_adj * 1e-3) / 1e9 / hbm,
+                             "note": "local kernels only (no all-reduce)"},
+    }
+    # dominant kernel = the forward march kernel (one launch == the whole evaluate! call)
+    roofline = {"kernel": "sg_eval3d_march_kernel<double,3,2,4,4> (evaluate!, one launch per call)",
+                "bound": "hbm", "achieved": ops["evaluate"]["achieved_GBs"], "peak": hbm, "unit": "GB/s",
+                "frac": ops["evaluate"]["frac_of_hbm_roofline"], "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+                "algorithmic_bytes_per_launch": nb_local, "traffic": args.traffic_bytes,
+                "traffic_source": "profiles/ (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"
+                if args.traffic_bytes else None,
+                "also": {"evaluate_adjoint_op_frac": ops["evaluate_adjoint"]["frac_of_hbm_roofline"]}}
+
+    # ---- end-to-end through the public API with HOST buffers -------------------------------------
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    flat = lambda t: t.permute(*reversed(range(t.dim()))).reshape(-1)       # contiguous view of a column-major array
+    h_cp = torch.empty(cp.numel(), dtype=cp.dtype).pin_memory()
+    h_cp.copy_(flat(cp).cpu())
+    h_ein = torch.empty(e_in.numel(), dtype=e_in.dtype).pin_memory()
+    h_ein.copy_(flat(e_in).cpu())
+    h_eval = torch.empty(grid.eval.numel(), dtype=cp.dtype).pin_memory()
+    h_grad = torch.empty(cp.numel(), dtype=cp.dtype).pin_memory()
+
+    def e2e_step():
+        flat(cp).copy_(h_cp, non_blocking=True)                 # H2D control points
+        S.evaluate_(grid)
+        h_eval.copy_(flat(grid.eval), non_blocking=True)        # D2H evaluated grid
+        flat(e_in).copy_(h_ein, non_blocking=True)              # H2D adjoint input
+        sh.evaluate_adjoint_(eval=e_in, control_points=grad)
+        h_grad.copy_(flat(grad), non_blocking=True)             # D2H gradient
+        torch.cuda.current_stream().synchronize()
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    dt = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    elem = cp.element_size()
+    e2e = {"value": values_per_step / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": e2e_steps,
+           "h2d_bytes_per_step": int((cp.numel() + e_in.numel()) * elem),
+           "d2h_bytes_per_step": int((grid.eval.numel() + cp.numel()) * elem),
+           "note": "per rank; pinned host buffers, copies + kernels + stream sync inside the timed region"}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ----------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, dts, cores = run_cpu_reference(steps=2, warmup=1, planes=args.cpu_planes)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step_sample": dts * 1e3,
+               "sample": f"slab of {args.cpu_planes}/512 planes of the same grid, evaluate!+adjoint, C/OpenMP restatement "
+                         f"of the reference algorithm (Julia not installed, the reference package cannot run)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": w["name"], "step": "evaluate! + evaluate_adjoint! (+ NCCL all-reduce of the gradient for N>1)",
+                           "sharding": f"sample grid in {world} slab(s) along axis 3, control points replicated",
+                           "l2": "inputs/outputs (1.07 GB per op) exceed the 126 MB L2; no flush needed"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "ops": ops,
+                "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-planes", type=int, default=32, help="slab thickness of the bounded CPU sample")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--traffic-bytes", type=float, default=None,
+                    help="DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -143,7 +143,7 @@ static int sg_evaluate_adjoint_impl(T *cp, int nin, const int64_t *n_samples, co
             g_sg_launches.fetch_add(1);
         }
         const unsigned gblocks = sg_blocks(a.cp_total, 128);
-        const unsigned sblocks = sg_blocks(a.n_total, 256);
+        const unsigned sblocks = (unsigned)std::min<int64_t>(sg_blocks(a.n_total, 256), 148 * 16);   // fallback: fixed small grid
         if (rational) {
             sg_adjoint_gather_kernel<T, true><<<gblocks, 128, 0, st>>>(cp, a, ss, hdr, eval, weights, denom);
             sg_adjoint_scatter_kernel<T, true><<<sblocks, 256, 0, st>>>(cp, a, hdr, eval, weights);

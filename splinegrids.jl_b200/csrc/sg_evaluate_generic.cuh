@@ -94,8 +94,9 @@ __global__ void __launch_bounds__(256) sg_adjoint_scatter_kernel(T *__restrict__
 {
     // With a header: run only if the prep kernel found non-monotone span indices.
     if (hdr_or_null != nullptr && !hdr_or_null->nonmonotone) return;
-    const int64_t lin = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (lin >= a.n_total) return;
+    // grid-stride loop: as a (normally idle) device-side fallback it is launched with a small, fixed grid
+    for (int64_t lin = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; lin < a.n_total;
+         lin += (int64_t)gridDim.x * blockDim.x) {
     int64_t J[SG_MAX_DIMS], base;
     sg_decode_sample(a, lin, J, base);
     T inv_denom = T(1);
@@ -124,5 +125,6 @@ __global__ void __launch_bounds__(256) sg_adjoint_scatter_kernel(T *__restrict__
                 if (o0 + q < a.nout) atomicAdd(cp + off + a.cp_total * (o0 + q), b * e[q]);
             sg_next_offset(a.nin, a.degree, I);
         }
+    }
     }
 }

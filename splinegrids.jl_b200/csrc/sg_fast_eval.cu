@@ -1,7 +1,12 @@
-// sg_fast.cu -- dispatch of the tiled sm_100a fast paths for evaluate! (and, in sg_fast_adjoint.cu, the adjoint).
+// sg_fast_eval.cu -- dispatch of the tiled sm_100a fast paths for evaluate! (kernels: sg_fast_eval.cuh).
 #include <cstdlib>
 
+#include <algorithm>
+#include <type_traits>
+
+#include "sg_evaluate_generic.cuh"
 #include "sg_fast.cuh"
+#include "sg_fast_adjoint.cuh"
 #include "sg_fast_eval.cuh"
 
 static int sg_env_int(const char *name, int dflt)
@@ -123,15 +128,5 @@ int sg_evaluate_fast(T *eval, const SgGridArgs<T> &a, const T *cp, const T *weig
     }
 }
 
-template <typename T>
-int sg_evaluate_adjoint_fast(T *, const SgGridArgs<T> &, const SgSpanStarts<T> &, SgAdjointHeader *, const T *,
-                             const T *, void *, cudaStream_t) { return SG_ERR_UNSUPPORTED; }
-
-size_t sg_adjoint_fast_scratch_bytes(int, const int64_t *, const int64_t *, int, const int *, int) { return 0; }
-
 template int sg_evaluate_fast<float>(float *, const SgGridArgs<float> &, const float *, const float *, cudaStream_t);
 template int sg_evaluate_fast<double>(double *, const SgGridArgs<double> &, const double *, const double *, cudaStream_t);
-template int sg_evaluate_adjoint_fast<float>(float *, const SgGridArgs<float> &, const SgSpanStarts<float> &, SgAdjointHeader *,
-                                             const float *, const float *, void *, cudaStream_t);
-template int sg_evaluate_adjoint_fast<double>(double *, const SgGridArgs<double> &, const SgSpanStarts<double> &, SgAdjointHeader *,
-                                              const double *, const double *, void *, cudaStream_t);
