@@ -87,11 +87,16 @@ size_t sg_adjoint_fast_scratch_bytes(int nin, const int64_t *n_samples, const in
 template <typename T, int P, int NT, bool RAT2D>
 static void sg_launch_adj_march_nt(const SgAdjPassArgs<T> &pa, int64_t outer, cudaStream_t st)
 {
-    constexpr int V = sizeof(T) == 4 ? 4 : 2;
-    const bool vec_ok = (pa.inner % V == 0) && (reinterpret_cast<uintptr_t>(pa.X) % 16 == 0) &&
+    constexpr int VV = sizeof(T) == 4 ? 4 : 2;
+    const bool vec_ok = (pa.inner % VV == 0) && (reinterpret_cast<uintptr_t>(pa.X) % 16 == 0) &&
                         (reinterpret_cast<uintptr_t>(pa.Y) % 16 == 0);
-    dim3 grid((unsigned)((pa.inner + 128 * V - 1) / (128 * V)), (unsigned)pa.nchunks, (unsigned)(outer / NT));
-    sg_adj_march_kernel<T, P, V, NT, RAT2D><<<grid, 128, 0, st>>>(pa, vec_ok);
+    if (vec_ok) {
+        dim3 grid((unsigned)((pa.inner + 128 * VV - 1) / (128 * VV)), (unsigned)pa.nchunks, (unsigned)(outer / NT));
+        sg_adj_march_kernel<T, P, VV, NT, RAT2D><<<grid, 128, 0, st>>>(pa);
+    } else {
+        dim3 grid((unsigned)((pa.inner + 127) / 128), (unsigned)pa.nchunks, (unsigned)(outer / NT));
+        sg_adj_march_kernel<T, P, 1, NT, RAT2D><<<grid, 128, 0, st>>>(pa);
+    }
     g_sg_launches.fetch_add(1);
 }
 
@@ -177,6 +182,17 @@ int sg_evaluate_adjoint_fast(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T
     if (avg_range >= 64) {
         if (rational) launch_b(std::integral_constant<int, 32>{}, std::true_type{});
         else launch_b(std::integral_constant<int, 32>{}, std::false_type{});
+    } else if (avg_range <= 24 && sg_env_int("SG_ADJ_PASSB_ROWS", 1)) {
+        // short ranges: per-thread weights in registers, many rows per block
+        const int rpb = 32;
+        dim3 rgrid(sg_blocks(a.n_cp[0], 128), (unsigned)((outerB + rpb - 1) / rpb));
+        if (rgrid.y > 65535) return SG_ERR_UNSUPPORTED;
+        if (rational)
+            sg_adj_first_dim_rows_kernel<T, 32, true><<<rgrid, 128, 0, st>>>(cp, X, a.table[0], a.index[0], ss.start[0], hdr, a.n_samples[0],
+                                                                            a.n_cp[0], outerB, a.degree[0], rpb, weights, a.cp_total);
+        else
+            sg_adj_first_dim_rows_kernel<T, 32, false><<<rgrid, 128, 0, st>>>(cp, X, a.table[0], a.index[0], ss.start[0], hdr, a.n_samples[0],
+                                                                             a.n_cp[0], outerB, a.degree[0], rpb, weights, a.cp_total);
     } else {
         if (rational) launch_b(std::integral_constant<int, 8>{}, std::true_type{});
         else launch_b(std::integral_constant<int, 8>{}, std::false_type{});

@@ -45,14 +45,27 @@ struct SgAdjPassArgs {
 // ---------------------------------------------------------------------------------------------
 // NT = independent outer channels (e.g. the Nout planes) processed by one thread: they share the table
 // rows, the span bookkeeping and -- for rational grids -- the denominators.
+// V = samples of the contiguous axis per thread; V > 1 requires inner % V == 0 and 16-byte aligned
+// arrays (checked by the dispatcher, which otherwise instantiates V = 1), so every active thread owns
+// exactly V columns and all loads/stores are full vectors.
+template <typename T, int V>
+__device__ __forceinline__ void sg_load_vec(const T *__restrict__ p, T (&x)[V])
+{
+    typename SgVecT<T, V>::type pk = __ldcs(reinterpret_cast<const typename SgVecT<T, V>::type *>(p));
+    const T *pq = reinterpret_cast<const T *>(&pk);
+#pragma unroll
+    for (int v = 0; v < V; ++v) x[v] = pq[v];
+}
+
 template <typename T, int P, int V, int NT, bool RAT2D>
-__global__ void __launch_bounds__(128) sg_adj_march_kernel(const __grid_constant__ SgAdjPassArgs<T> a, bool vec_ok)
+__global__ void __launch_bounds__(128) sg_adj_march_kernel(const __grid_constant__ SgAdjPassArgs<T> a)
 {
     if (a.hdr->nonmonotone) return;
     __shared__ __align__(16) T bs[SG_ADJ_PIECE * (P + 1)];
     __shared__ int ss[SG_ADJ_PIECE];
     constexpr int E = 1;
     constexpr int WD = P + 1 + E;
+    constexpr int U = NT >= 2 ? 4 : 8;                                 // steps whose loads are issued together
 
     const int64_t q0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
     const int c = blockIdx.y;
@@ -61,14 +74,13 @@ __global__ void __launch_bounds__(128) sg_adj_march_kernel(const __grid_constant
     const int s_hi = (int)min((int64_t)s_lo + a.G, a.c_d + 1);         // one past the last span
     const int64_t j_lo = a.span_start[s_lo], j_hi = a.span_start[s_hi];
     const bool active = q0 < a.inner;
-    const int nv = active ? (int)min((int64_t)V, a.inner - q0) : 0;
-    const bool vec = vec_ok && nv == V;
     const int rows = a.G + P;
+    const int64_t inner = a.inner;
 
-    const T *__restrict__ xp = a.X + q0 + a.inner * (j_lo + a.n_d * r);
-    T *__restrict__ yp = a.Y + q0 + a.inner * ((int64_t)rows * (c + (int64_t)a.nchunks * r));
-    const int64_t x_ch = a.inner * a.n_d;                              // channel strides
-    const int64_t y_ch = a.inner * (int64_t)rows * a.nchunks;
+    const T *__restrict__ xp = a.X + q0 + inner * (j_lo + a.n_d * r);
+    T *__restrict__ yp = a.Y + q0 + inner * ((int64_t)rows * (c + (int64_t)a.nchunks * r));   // oldest live row
+    const int64_t x_ch = inner * a.n_d;                                // channel strides
+    const int64_t y_ch = inner * (int64_t)rows * a.nchunks;
 
     T acc[NT][V][P + 1];
 #pragma unroll
@@ -78,7 +90,6 @@ __global__ void __launch_bounds__(128) sg_adj_march_kernel(const __grid_constant
 #pragma unroll
             for (int k = 0; k <= P; ++k) acc[t][v][k] = T(0);
     int cur = s_lo;
-    int row = 0;   // local index of the oldest live row (1-based control index cur-P  <->  row)
 
     // rational 2-D: forward march of the weights for this thread's V columns (cf. sg_eval2d_march_kernel)
     T W1[V][WD];
@@ -87,7 +98,7 @@ __global__ void __launch_bounds__(128) sg_adj_march_kernel(const __grid_constant
     bool reg1 = true;
     if (RAT2D && active) {
         int min1;
-        reg1 = sg_expand_weights<T, P, V, E>(a.table1, a.index1, a.inner, q0, W1, min1);
+        reg1 = sg_expand_weights<T, P, V, E>(a.table1, a.index1, inner, q0, W1, min1);
 #pragma unroll
         for (int q = 0; q < WD; ++q) col1[q] = min((int64_t)min1 + q, a.c1 - 1);
     }
@@ -102,11 +113,12 @@ __global__ void __launch_bounds__(128) sg_adj_march_kernel(const __grid_constant
                 for (int v = 0; v < V; ++v) out[v] = fma(W1[v][aq], w, out[v]);
             }
         } else {   // irregular thread: direct per-column sums
-            for (int v = 0; v < nv; ++v) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
                 const int64_t j1 = q0 + v;
                 const int64_t b1 = sg_ldg(a.index1 + j1) - P - 1;
                 T sacc = T(0);
-                for (int k = 0; k <= P; ++k) sacc = fma(sg_ldg(a.table1 + j1 + a.inner * k), sg_ldg(a.weights + i2 * a.c1 + b1 + k), sacc);
+                for (int k = 0; k <= P; ++k) sacc = fma(sg_ldg(a.table1 + j1 + inner * k), sg_ldg(a.weights + i2 * a.c1 + b1 + k), sacc);
                 out[v] = sacc;
             }
         }
@@ -121,15 +133,14 @@ __global__ void __launch_bounds__(128) sg_adj_march_kernel(const __grid_constant
         }
     }
 
-    auto emit_oldest = [&]() {   // write row `row` (complete or chunk-partial) and slide the window
+    // write the oldest live row (complete, or chunk-partial) and slide the window by one span
+    auto emit_oldest = [&]() {
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-            if (active) {
-                T o[V];
+            T o[V];
 #pragma unroll
-                for (int v = 0; v < V; ++v) o[v] = acc[t][v][0];
-                sg_store_vec<T, V>(yp + y_ch * t + a.inner * row, o, vec, nv);
-            }
+            for (int v = 0; v < V; ++v) o[v] = acc[t][v][0];
+            sg_store_vec<T, V>(yp + y_ch * t, o, true, V);
 #pragma unroll
             for (int v = 0; v < V; ++v) {
 #pragma unroll
@@ -137,9 +148,9 @@ __global__ void __launch_bounds__(128) sg_adj_march_kernel(const __grid_constant
                 acc[t][v][P] = T(0);
             }
         }
-        ++row;
+        yp += inner;
         ++cur;
-        if (RAT2D && active && cur <= (int)a.c_d) {
+        if (RAT2D && cur <= (int)a.c_d) {
             T o[V];
             wrow((int64_t)cur - 1, o);
 #pragma unroll
@@ -149,6 +160,34 @@ __global__ void __launch_bounds__(128) sg_adj_march_kernel(const __grid_constant
                 Tw[v][P] = o[v];
             }
         }
+    };
+
+    // one marching step: sample s of the staged piece, values x[NT][V]
+    auto step = [&](int s, T (&x)[NT][V]) {
+        const int sp = ss[s];
+        if (cur < sp) {
+            do emit_oldest(); while (cur < sp);
+        }
+        T b[P + 1];
+#pragma unroll
+        for (int k = 0; k <= P; ++k) b[k] = bs[s * (P + 1) + k];
+        if (RAT2D) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                T den = b[0] * Tw[v][0];
+#pragma unroll
+                for (int k = 1; k <= P; ++k) den = fma(b[k], Tw[v][k], den);
+                const T inv = T(1) / den;
+#pragma unroll
+                for (int t = 0; t < NT; ++t) x[t][v] *= inv;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+#pragma unroll
+            for (int k = 0; k <= P; ++k)
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc[t][v][k] = fma(b[k], x[t][v], acc[t][v][k]);
     };
 
     for (int64_t jp = j_lo; jp < j_hi; jp += SG_ADJ_PIECE) {
@@ -161,72 +200,39 @@ __global__ void __launch_bounds__(128) sg_adj_march_kernel(const __grid_constant
         }
         __syncthreads();
         if (!active) continue;
-        // software pipeline: issue the loads of U steps back to back (memory-level parallelism), then consume
-        constexpr int U = NT > 2 ? 4 : (NT == 2 ? 4 : 8);
-        for (int s0 = 0; s0 < np; s0 += U) {
+        int s = 0;
+        // full groups of U steps: all loads first (memory-level parallelism), no bounds checks
+        for (; s + U <= np; s += U) {
             T xs[U][NT][V];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (s0 + u < np) {
 #pragma unroll
-                    for (int t = 0; t < NT; ++t) {
-                        const T *__restrict__ xq = xp + a.inner * u + x_ch * t;
-                        if (vec) {
-                            typename SgVecT<T, V>::type pk = __ldcs(reinterpret_cast<const typename SgVecT<T, V>::type *>(xq));
-                            const T *pq = reinterpret_cast<const T *>(&pk);
-#pragma unroll
-                            for (int v = 0; v < V; ++v) xs[u][t][v] = pq[v];
-                        } else {
-#pragma unroll
-                            for (int v = 0; v < V; ++v) xs[u][t][v] = v < nv ? __ldcs(xq + v) : T(0);
-                        }
-                    }
-                }
+                for (int t = 0; t < NT; ++t) sg_load_vec<T, V>(xp + x_ch * t, xs[u][t]);
+                xp += inner;
             }
-            xp += a.inner * U;
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int s = s0 + u;
-                if (s < np) {
-                    const int sp = ss[s];
-                    while (cur < sp) emit_oldest();
-                    T b[P + 1];
+            for (int u = 0; u < U; ++u) step(s + u, xs[u]);
+        }
+        for (; s < np; ++s) {   // tail
+            T x1[NT][V];
 #pragma unroll
-                    for (int k = 0; k <= P; ++k) b[k] = bs[s * (P + 1) + k];
-                    if (RAT2D) {
-#pragma unroll
-                        for (int v = 0; v < V; ++v) {
-                            T den = b[0] * Tw[v][0];
-#pragma unroll
-                            for (int k = 1; k <= P; ++k) den = fma(b[k], Tw[v][k], den);
-                            const T inv = T(1) / den;
-#pragma unroll
-                            for (int t = 0; t < NT; ++t) xs[u][t][v] *= inv;
-                        }
-                    }
-#pragma unroll
-                    for (int t = 0; t < NT; ++t)
-#pragma unroll
-                        for (int k = 0; k <= P; ++k)
-#pragma unroll
-                            for (int v = 0; v < V; ++v) acc[t][v][k] = fma(b[k], xs[u][t][v], acc[t][v][k]);
-                }
-            }
+            for (int t = 0; t < NT; ++t) sg_load_vec<T, V>(xp + x_ch * t, x1[t]);
+            xp += inner;
+            step(s, x1);
         }
     }
+    if (!active) return;
     // flush: finish the chunk's spans, then the P still-live rows
     while (cur < s_hi) emit_oldest();
-    if (active) {
 #pragma unroll
-        for (int t = 0; t < NT; ++t)
+    for (int t = 0; t < NT; ++t)
 #pragma unroll
-            for (int k = 0; k < P; ++k) {
-                T o[V];
+        for (int k = 0; k < P; ++k) {
+            T o[V];
 #pragma unroll
-                for (int v = 0; v < V; ++v) o[v] = acc[t][v][k];
-                sg_store_vec<T, V>(yp + y_ch * t + a.inner * (row + k), o, vec, nv);
-            }
-    }
+            for (int v = 0; v < V; ++v) o[v] = acc[t][v][k];
+            sg_store_vec<T, V>(yp + y_ch * t + inner * k, o, true, V);
+        }
 }
 
 // combine chunk partials: Y[q, i, r] = sum_c P[q, i - (c*G + 1), c, r]   (i 1-based control index).
@@ -303,5 +309,79 @@ __global__ void __launch_bounds__(256) sg_adj_first_dim_kernel(T *__restrict__ c
     if (valid && lane == 0) {
         if (RATIONAL) acc *= sg_ldg(weights + lin % cp_total);
         cp[lin] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass B, short-range regime (few samples per knot span): one thread per control index i keeps its
+// <= RMAX gather weights in registers and loops over many rows r (the weights do not depend on r).
+// Lanes own consecutive i, so a warp reads one contiguous stretch of the row (L1-resident after the first
+// touch).  A thread whose range is longer than RMAX falls back to table look-ups (still correct).
+// ---------------------------------------------------------------------------------------------
+template <typename T, int RMAX, bool RATIONAL>
+__global__ void __launch_bounds__(128) sg_adj_first_dim_rows_kernel(T *__restrict__ cp, const T *__restrict__ X, const T *__restrict__ table,
+                                                                    const int32_t *__restrict__ index, const int32_t *__restrict__ span_start,
+                                                                    const SgAdjointHeader *hdr, int64_t n1, int64_t c1, int64_t outer, int P,
+                                                                    int rows_per_block, const T *__restrict__ weights, int64_t cp_total)
+{
+    if (hdr->nonmonotone) return;
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // 0-based control index
+    if (i0 >= c1) return;
+    const int64_t i = i0 + 1;
+    const int64_t s0 = i > P + 1 ? i : P + 1;
+    const int64_t s1 = i + P < c1 ? i + P : c1;
+    const int64_t lo = span_start[s0], hi = span_start[s1 + 1];
+    const int len = (int)(hi - lo);
+    const int64_t r_lo = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t r_hi = min(r_lo + rows_per_block, outer);
+    if (len > RMAX) {   // long range: direct look-ups
+        for (int64_t r = r_lo; r < r_hi; ++r) {
+            T acc = T(0);
+            for (int64_t j = lo; j < hi; ++j) {
+                const int k = (int)(i - sg_ldg(index + j) + P);
+                acc = fma(sg_ldg(table + j + n1 * k), sg_ldg(X + j + n1 * r), acc);
+            }
+            const int64_t lin = i0 + c1 * r;
+            cp[lin] = RATIONAL ? acc * sg_ldg(weights + lin % cp_total) : acc;
+        }
+        return;
+    }
+    T w[RMAX];
+#pragma unroll
+    for (int t = 0; t < RMAX; ++t) {
+        const int64_t j = lo + t;
+        if (t < len) {
+            const int k = (int)(i - sg_ldg(index + j) + P);
+            w[t] = sg_ldg(table + j + n1 * k);
+        } else {
+            w[t] = T(0);
+        }
+    }
+    const int64_t jmax = n1 - 1;
+    int64_t r = r_lo;
+    for (; r + 1 < r_hi; r += 2) {   // two rows per iteration for ILP
+        const T *__restrict__ x0 = X + n1 * r, *__restrict__ x1 = x0 + n1;
+        T a0 = T(0), a1 = T(0);
+#pragma unroll
+        for (int t = 0; t < RMAX; ++t) {
+            if (t < len) {   // len is warp-nearly-uniform; padded tail skipped
+                const int64_t j = min(lo + t, jmax);
+                a0 = fma(w[t], sg_ldg(x0 + j), a0);
+                a1 = fma(w[t], sg_ldg(x1 + j), a1);
+            }
+        }
+        const int64_t lin = i0 + c1 * r;
+        if (RATIONAL) { a0 *= sg_ldg(weights + lin % cp_total); a1 *= sg_ldg(weights + (lin + c1) % cp_total); }
+        cp[lin] = a0;
+        cp[lin + c1] = a1;
+    }
+    if (r < r_hi) {
+        const T *__restrict__ x0 = X + n1 * r;
+        T a0 = T(0);
+#pragma unroll
+        for (int t = 0; t < RMAX; ++t)
+            if (t < len) a0 = fma(w[t], sg_ldg(x0 + min(lo + t, jmax)), a0);
+        const int64_t lin = i0 + c1 * r;
+        cp[lin] = RATIONAL ? a0 * sg_ldg(weights + lin % cp_total) : a0;
     }
 }
