@@ -91,8 +91,12 @@ static inline int sg_fill_grid_args(SgGridArgs<T> &a, int nin, const int64_t *n_
 // Adjoint workspace header (first 256 bytes of the workspace)
 struct SgAdjointHeader {
     int nonmonotone;  // set to 1 by the prep kernel if any dimension's span indices decrease
-    int pad[63];
+    int fused_bad;    // (unused) kept for layout stability
+    int pad[62];
 };
+// Fused adjoint: control-index slots reserved per warp tile of TS = 32*V samples of dimension 1.  A tile
+// touches at most TS + p control indices (every sample in its own span), p <= 5 -> TS + 8 (keeps 16-byte alignment).
+#define SG_ADJ_SLOT_PAD 8
 
 // Read-only (non-coherent) load helper
 template <typename T>

@@ -77,13 +77,6 @@ static bool sg_adjoint_fast_supported(int nin, const int *degree, bool rational)
     return true;
 }
 
-size_t sg_adjoint_fast_scratch_bytes(int nin, const int64_t *n_samples, const int64_t *n_cp, int nout, const int *degree,
-                                     int elem_size)
-{
-    if (!sg_adjoint_fast_supported(nin, degree, false)) return 0;
-    return sg_adjoint_plan(nin, n_samples, n_cp, nout, degree, elem_size).bytes;
-}
-
 template <typename T, int P, int NT, bool RAT2D>
 static void sg_launch_adj_march_nt(const SgAdjPassArgs<T> &pa, int64_t outer, cudaStream_t st)
 {
@@ -116,22 +109,47 @@ static void sg_launch_adj_march(const SgAdjPassArgs<T> &pa, int64_t outer, int n
     }
 }
 
+// ---- one generic pass A (+ chunk combine) ---------------------------------------------------------
 template <typename T>
-int sg_evaluate_adjoint_fast(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &ss, SgAdjointHeader *hdr,
-                             const T *eval, const T *weights, void *scratch, cudaStream_t st)
+static void sg_run_pass_a(const SgAdjPass &ps, SgAdjPassArgs<T> &pa, T *out, T *part, bool rat_here, int path,
+                          const SgAdjointHeader *hdr, cudaStream_t st)
+{
+    const int nt = (rat_here && ps.outer <= 4) ? (int)ps.outer : 1;   // shares the denominators between the outputs
+    if (rat_here) {
+        switch (ps.P) {
+            case 1: sg_launch_adj_march<T, 1, true>(pa, ps.outer, nt, st); break;
+            case 2: sg_launch_adj_march<T, 2, true>(pa, ps.outer, nt, st); break;
+            default: sg_launch_adj_march<T, 3, true>(pa, ps.outer, nt, st); break;
+        }
+    } else {
+        switch (ps.P) {
+            case 1: sg_launch_adj_march<T, 1, false>(pa, ps.outer, nt, st); break;
+            case 2: sg_launch_adj_march<T, 2, false>(pa, ps.outer, nt, st); break;
+            case 3: sg_launch_adj_march<T, 3, false>(pa, ps.outer, nt, st); break;
+            case 4: sg_launch_adj_march<T, 4, false>(pa, ps.outer, nt, st); break;
+            default: sg_launch_adj_march<T, 5, false>(pa, ps.outer, nt, st); break;
+        }
+    }
+    if (ps.nchunks > 1) {
+        constexpr int VC = sizeof(T) == 4 ? 4 : 2;
+        const bool vec_ok = (ps.inner % VC == 0);
+        dim3 cgrid((unsigned)((ps.inner + 128 * VC - 1) / (128 * VC)), (unsigned)ps.c_d, (unsigned)ps.outer);
+        sg_adj_combine_kernel<T, VC><<<cgrid, 128, 0, st>>>(out, part, hdr, ps.inner, ps.c_d, ps.G, ps.nchunks, ps.P, vec_ok, path);
+        g_sg_launches.fetch_add(1);
+    }
+}
+
+// ---- multi-pass pipeline ---------------------------------------------------------------------------
+template <typename T>
+static int sg_run_multipass(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &ss, SgAdjointHeader *hdr, const T *eval,
+                            const T *weights, char *ws, int path, cudaStream_t st)
 {
     const bool rational = weights != nullptr;
-    if (!sg_adjoint_fast_supported(a.nin, a.degree, rational)) return SG_ERR_UNSUPPORTED;
-    if (g_sg_policy != 2 && a.n_total < 32768) return SG_ERR_UNSUPPORTED;
     const SgAdjPlan pl = sg_adjoint_plan(a.nin, a.n_samples, a.n_cp, a.nout, a.degree, (int)sizeof(T));
     for (int k = 0; k < pl.npassA; ++k) {
         const SgAdjPass &ps = pl.pass[k];
-        if (ps.outer > 65535 || ps.nchunks > 65535 || (ps.nchunks > 1 && ps.c_d > 65535)) return SG_ERR_UNSUPPORTED;   // grid.y / grid.z limits
+        if (ps.outer > 65535 || ps.nchunks > 65535 || (ps.nchunks > 1 && ps.c_d > 65535)) return SG_ERR_UNSUPPORTED;
     }
-    char *ws = static_cast<char *>(scratch);
-    // zero fill (src/adjoint.jl:61): needed only if the prep kernel flags non-monotone spans (scatter path)
-    SG_CUDA(cudaMemsetAsync(cp, 0, (size_t)a.cp_total * a.nout * sizeof(T), st));
-
     const T *X = eval;
     for (int k = 0; k < pl.npassA; ++k) {
         const SgAdjPass &ps = pl.pass[k];
@@ -140,32 +158,10 @@ int sg_evaluate_adjoint_fast(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T
         SgAdjPassArgs<T> pa{};
         pa.X = X; pa.Y = part; pa.table = a.table[ps.d]; pa.index = a.index[ps.d]; pa.span_start = ss.start[ps.d];
         pa.hdr = hdr; pa.inner = ps.inner; pa.n_d = ps.n_d; pa.c_d = ps.c_d; pa.G = ps.G; pa.nchunks = ps.nchunks;
-        // the first pass handles the (<= 4) output planes of one column in one thread
-        const bool rat_here = rational && k == 0;
-        const int nt = (rat_here && ps.outer <= 4) ? (int)ps.outer : 1;   // shares the denominators between the outputs   // nin == 2: the first pass marches dim 2 over columns of dim 1
+        pa.path = path;
+        const bool rat_here = rational && k == 0;   // nin == 2: the first pass marches dim 2 over columns of dim 1
         if (rat_here) { pa.weights = weights; pa.table1 = a.table[0]; pa.index1 = a.index[0]; pa.c1 = a.n_cp[0]; }
-        if (rat_here) {
-            switch (ps.P) {
-                case 1: sg_launch_adj_march<T, 1, true>(pa, ps.outer, nt, st); break;
-                case 2: sg_launch_adj_march<T, 2, true>(pa, ps.outer, nt, st); break;
-                default: sg_launch_adj_march<T, 3, true>(pa, ps.outer, nt, st); break;
-            }
-        } else {
-            switch (ps.P) {
-                case 1: sg_launch_adj_march<T, 1, false>(pa, ps.outer, nt, st); break;
-                case 2: sg_launch_adj_march<T, 2, false>(pa, ps.outer, nt, st); break;
-                case 3: sg_launch_adj_march<T, 3, false>(pa, ps.outer, nt, st); break;
-                case 4: sg_launch_adj_march<T, 4, false>(pa, ps.outer, nt, st); break;
-                default: sg_launch_adj_march<T, 5, false>(pa, ps.outer, nt, st); break;
-            }
-        }
-        if (ps.nchunks > 1) {
-            constexpr int VC = sizeof(T) == 4 ? 4 : 2;
-            const bool vec_ok = (ps.inner % VC == 0);
-            dim3 cgrid((unsigned)((ps.inner + 128 * VC - 1) / (128 * VC)), (unsigned)ps.c_d, (unsigned)ps.outer);
-            sg_adj_combine_kernel<T, VC><<<cgrid, 128, 0, st>>>(out, part, hdr, ps.inner, ps.c_d, ps.G, ps.nchunks, ps.P, vec_ok);
-            g_sg_launches.fetch_add(1);
-        }
+        sg_run_pass_a<T>(ps, pa, out, part, rat_here, path, hdr, st);
         X = out;
     }
     // pass B: first dimension
@@ -177,27 +173,166 @@ int sg_evaluate_adjoint_fast(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T
         const unsigned gy = (unsigned)std::min<int64_t>(outerB, 32768);
         dim3 bgrid(sg_blocks(a.n_cp[0], 256 / L), gy, (unsigned)((outerB + gy - 1) / gy));
         sg_adj_first_dim_kernel<T, L, R><<<bgrid, 256, 0, st>>>(cp, X, a.table[0], a.index[0], ss.start[0], hdr, a.n_samples[0],
-                                                                  a.n_cp[0], outerB, a.degree[0], weights, a.cp_total);
+                                                                a.n_cp[0], outerB, a.degree[0], weights, a.cp_total, path);
     };
     if (avg_range >= 64) {
         if (rational) launch_b(std::integral_constant<int, 32>{}, std::true_type{});
         else launch_b(std::integral_constant<int, 32>{}, std::false_type{});
-    } else if (avg_range <= 24 && sg_env_int("SG_ADJ_PASSB_ROWS", 1)) {
+    } else if (avg_range <= 18 && sg_env_int("SG_ADJ_PASSB_ROWS", 1)) {
         // short ranges: per-thread weights in registers, many rows per block
-        const int rpb = 32;
+        const int rpb = sg_env_int("SG_ADJ_RPB", 8);
         dim3 rgrid(sg_blocks(a.n_cp[0], 128), (unsigned)((outerB + rpb - 1) / rpb));
         if (rgrid.y > 65535) return SG_ERR_UNSUPPORTED;
         if (rational)
-            sg_adj_first_dim_rows_kernel<T, 32, true><<<rgrid, 128, 0, st>>>(cp, X, a.table[0], a.index[0], ss.start[0], hdr, a.n_samples[0],
-                                                                            a.n_cp[0], outerB, a.degree[0], rpb, weights, a.cp_total);
+            sg_adj_first_dim_rows_kernel<T, 20, true><<<rgrid, 128, 0, st>>>(cp, X, a.table[0], a.index[0], ss.start[0], hdr, a.n_samples[0],
+                                                                            a.n_cp[0], outerB, a.degree[0], rpb, weights, a.cp_total, path);
         else
-            sg_adj_first_dim_rows_kernel<T, 32, false><<<rgrid, 128, 0, st>>>(cp, X, a.table[0], a.index[0], ss.start[0], hdr, a.n_samples[0],
-                                                                             a.n_cp[0], outerB, a.degree[0], rpb, weights, a.cp_total);
+            sg_adj_first_dim_rows_kernel<T, 20, false><<<rgrid, 128, 0, st>>>(cp, X, a.table[0], a.index[0], ss.start[0], hdr, a.n_samples[0],
+                                                                             a.n_cp[0], outerB, a.degree[0], rpb, weights, a.cp_total, path);
     } else {
         if (rational) launch_b(std::integral_constant<int, 8>{}, std::true_type{});
         else launch_b(std::integral_constant<int, 8>{}, std::false_type{});
     }
     g_sg_launches.fetch_add(1);
+    return SG_OK;
+}
+
+// ---- fused pipeline: plan -----------------------------------------------------------------------------
+struct SgFusedPlan {
+    bool ok;
+    int n_tiles, tile_size, n_slots;
+    int64_t M;                   // product of the middle sample dimensions
+    size_t y_off;                // output of the fused first pass
+    int npassA;                  // middle passes (dims D-2 .. 1)
+    SgAdjPass pass[SG_MAX_DIMS];
+    size_t bytes;
+};
+
+static SgFusedPlan sg_adjoint_fused_plan(int nin, const int64_t *n_samples, const int64_t *n_cp, int nout, const int *degree,
+                                         int elem_size, bool rational)
+{
+    SgFusedPlan fp{};
+    const int V = elem_size == 4 ? 4 : 2;
+    fp.tile_size = 32 * V;
+    fp.ok = false;
+    if (rational || nin < 2 || sg_env_int("SG_ADJ_FUSED", 0) == 0) return fp;
+    if (degree[nin - 1] > 3) return fp;                              // instantiated degrees of the marching axis
+    if (n_samples[0] % fp.tile_size != 0) return fp;
+    fp.n_tiles = (int)(n_samples[0] / fp.tile_size);
+    fp.n_slots = fp.tile_size + SG_ADJ_SLOT_PAD;
+    int64_t inner = 1;
+    for (int e = 0; e < nin - 1; ++e) inner *= n_samples[e];
+    if ((inner / V) * nout < 24576) return fp;                        // too few columns: the chunked multi-pass path is better
+    if (nout > 65535) return fp;
+    fp.M = inner / n_samples[0];
+    size_t off = 0;
+    fp.y_off = off;
+    off += sg_al256((size_t)fp.n_slots * fp.n_tiles * fp.M * n_cp[nin - 1] * nout * elem_size);
+    int64_t outer = (int64_t)nout * n_cp[nin - 1];
+    for (int d = nin - 2; d >= 1; --d) {
+        SgAdjPass &ps = fp.pass[fp.npassA++];
+        ps.d = d;
+        ps.inner = (int64_t)fp.n_slots * fp.n_tiles;
+        for (int e = 1; e < d; ++e) ps.inner *= n_samples[e];
+        ps.n_d = n_samples[d];
+        ps.c_d = n_cp[d];
+        ps.outer = outer;
+        ps.P = degree[d];
+        const int64_t nspans = ps.c_d - ps.P;
+        const int64_t threads = ((ps.inner + V - 1) / V) * outer;
+        int64_t nchunks = 1;
+        if (threads < 65536) nchunks = std::min<int64_t>(nspans, (148 * 8 * 128 + threads - 1) / threads);
+        ps.G = (int)((nspans + nchunks - 1) / nchunks);
+        ps.nchunks = (int)((nspans + ps.G - 1) / ps.G);
+        ps.part_off = off;
+        if (ps.nchunks > 1) off += sg_al256((size_t)ps.inner * (ps.G + ps.P) * ps.nchunks * outer * elem_size);
+        ps.out_off = off;
+        off += sg_al256((size_t)ps.inner * ps.c_d * outer * elem_size);
+        if (ps.outer > 65535 || ps.nchunks > 65535 || (ps.nchunks > 1 && ps.c_d > 65535)) return fp;
+        outer *= ps.c_d;
+    }
+    fp.bytes = off;
+    fp.ok = true;
+    return fp;
+}
+
+size_t sg_adjoint_fast_scratch_bytes(int nin, const int64_t *n_samples, const int64_t *n_cp, int nout, const int *degree,
+                                     int elem_size)
+{
+    if (!sg_adjoint_fast_supported(nin, degree, false)) return 0;
+    const size_t a = sg_adjoint_plan(nin, n_samples, n_cp, nout, degree, elem_size).bytes;
+    const SgFusedPlan fp = sg_adjoint_fused_plan(nin, n_samples, n_cp, nout, degree, elem_size, false);
+    return std::max(a, fp.ok ? fp.bytes : (size_t)0);   // the two pipelines never run together: they share the scratch
+}
+
+template <typename T, int P>
+static void sg_launch_fused_first(const SgAdjPassArgs<T> &pa, int64_t outer, cudaStream_t st)
+{
+    constexpr int V = sizeof(T) == 4 ? 4 : 2;
+    dim3 grid((unsigned)((pa.inner + 128 * V - 1) / (128 * V)), 1, (unsigned)outer);
+    sg_adj_march_j1_kernel<T, P, V, 24, 4><<<grid, 128, 0, st>>>(pa);
+    g_sg_launches.fetch_add(1);
+}
+
+template <typename T>
+static int sg_run_fused(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &ss, SgAdjointHeader *hdr, const T *eval,
+                        const SgFusedPlan &fp, char *ws, cudaStream_t st)
+{
+    const int D = a.nin;
+    SgAdjPassArgs<T> pa{};
+    T *Y = reinterpret_cast<T *>(ws + fp.y_off);
+    pa.X = eval; pa.Y = Y; pa.table = a.table[D - 1]; pa.index = a.index[D - 1]; pa.span_start = ss.start[D - 1];
+    pa.hdr = hdr; pa.inner = a.n_total / a.n_samples[D - 1]; pa.n_d = a.n_samples[D - 1]; pa.c_d = a.n_cp[D - 1];
+    pa.G = (int)(a.n_cp[D - 1] - a.degree[D - 1]); pa.nchunks = 1; pa.path = SG_PATH_FUSED;
+    pa.table1 = a.table[0]; pa.index1 = a.index[0]; pa.c1 = a.n_cp[0]; pa.n1 = a.n_samples[0]; pa.P1 = a.degree[0];
+    pa.tile_lo = ss.tile_lo; pa.tile_ni = ss.tile_ni; pa.n_tiles = fp.n_tiles; pa.n_slots = fp.n_slots; pa.span_start1 = ss.start[0];
+    switch (a.degree[D - 1]) {
+        case 1: sg_launch_fused_first<T, 1>(pa, a.nout, st); break;
+        case 2: sg_launch_fused_first<T, 2>(pa, a.nout, st); break;
+        default: sg_launch_fused_first<T, 3>(pa, a.nout, st); break;
+    }
+    const T *X = Y;
+    for (int k = 0; k < fp.npassA; ++k) {
+        const SgAdjPass &ps = fp.pass[k];
+        T *out = reinterpret_cast<T *>(ws + ps.out_off);
+        T *part = ps.nchunks > 1 ? reinterpret_cast<T *>(ws + ps.part_off) : out;
+        SgAdjPassArgs<T> pm{};
+        pm.X = X; pm.Y = part; pm.table = a.table[ps.d]; pm.index = a.index[ps.d]; pm.span_start = ss.start[ps.d];
+        pm.hdr = hdr; pm.inner = ps.inner; pm.n_d = ps.n_d; pm.c_d = ps.c_d; pm.G = ps.G; pm.nchunks = ps.nchunks;
+        pm.path = SG_PATH_FUSED; pm.tile_ni = ss.tile_ni; pm.n_tiles = fp.n_tiles; pm.n_slots = fp.n_slots;
+        sg_run_pass_a<T>(ps, pm, out, part, false, SG_PATH_FUSED, hdr, st);
+        X = out;
+    }
+    const int64_t rest = a.cp_total / a.n_cp[0] * a.nout;
+    const unsigned gy = (unsigned)std::min<int64_t>(rest, 32768);
+    dim3 tgrid(sg_blocks(a.n_cp[0], 128), gy, (unsigned)((rest + gy - 1) / gy));
+    sg_adj_tile_combine_kernel<T><<<tgrid, 128, 0, st>>>(cp, X, ss.tile_lo, ss.tile_ni, fp.n_tiles, fp.n_slots, a.n_cp[0], rest, hdr, SG_PATH_FUSED);
+    g_sg_launches.fetch_add(1);
+    return SG_OK;
+}
+
+template <typename T>
+int sg_evaluate_adjoint_fast(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &ss, SgAdjointHeader *hdr,
+                             const T *eval, const T *weights, void *scratch, cudaStream_t st)
+{
+    const bool rational = weights != nullptr;
+    if (!sg_adjoint_fast_supported(a.nin, a.degree, rational)) return SG_ERR_UNSUPPORTED;
+    if (g_sg_policy != 2 && a.n_total < 32768) return SG_ERR_UNSUPPORTED;
+    char *ws = static_cast<char *>(scratch);
+    // zero fill (src/adjoint.jl:61): needed only if the prep kernel flags non-monotone spans (scatter path)
+    SG_CUDA(cudaMemsetAsync(cp, 0, (size_t)a.cp_total * a.nout * sizeof(T), st));
+
+    SgFusedPlan fp = sg_adjoint_fused_plan(a.nin, a.n_samples, a.n_cp, a.nout, a.degree, (int)sizeof(T), rational);
+    if (fp.ok && reinterpret_cast<uintptr_t>(eval) % 16 != 0) fp.ok = false;
+    int rc;
+    if (fp.ok) {
+        rc = sg_run_fused<T>(cp, a, ss, hdr, eval, fp, ws, st);
+        g_sg_last_variant = "adjoint_fused_j1";
+    } else {
+        rc = sg_run_multipass<T>(cp, a, ss, hdr, eval, weights, ws, SG_PATH_MULTIPASS, st);
+        g_sg_last_variant = rational ? "adjoint_passes_rational2d" : "adjoint_passes";
+    }
+    if (rc != SG_OK) return rc;
     // non-monotone span indices (decided on device): the reference's atomic scatter
     const unsigned sblocks = (unsigned)std::min<int64_t>(sg_blocks(a.n_total, 256), 148 * 16);   // fallback: fixed small grid
     if (rational)
@@ -205,7 +340,6 @@ int sg_evaluate_adjoint_fast(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T
     else
         sg_adjoint_scatter_kernel<T, false><<<sblocks, 256, 0, st>>>(cp, a, hdr, eval, weights);
     g_sg_launches.fetch_add(1);
-    g_sg_last_variant = rational ? "adjoint_passes_rational2d" : "adjoint_passes";
     cudaError_t e = cudaPeekAtLastError();
     return e == cudaSuccess ? SG_OK : (int)e;
 }

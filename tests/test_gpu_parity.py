@@ -160,6 +160,11 @@ CASES = [
     ((16, 16, 16), (3, 3, 3), (40, 36, 44), 1, "Float64", 0, False),
     ((16, 16), (3, 3), (128, 96), 3, "Float32", 0, True),
     ((20, 3), (2, 2), (3, 50), 2, "Float64", 0, False),                   # fewer samples than spans
+    # shapes eligible for the fused adjoint (n_1 multiple of the 32-lane tile, enough columns)
+    ((20, 11, 9), (3, 3, 3), (128, 400, 20), 1, "Float64", 0, False),
+    ((40, 9, 7), (2, 3, 2), (256, 400, 12), 2, "Float32", 1, False),
+    ((100, 8, 6), (2, 2, 2), (128, 400, 20), 1, "Float64", 0, False),     # > 32 control indices per tile: device-side fallback
+    ((12, 6, 9, 5), (3, 2, 3, 1), (64, 20, 40, 5), 2, "Float64", 0, False),   # Nin = 4 through the fused pipeline
 ]
 
 
@@ -191,6 +196,26 @@ def test_evaluate_and_adjoint_vs_oracle(S, case, policy):
             assert max_rel_err(S.to_numpy(g), gref) <= 10 * tol, (der, S.last_variant())
     finally:
         S.set_kernel_policy(0)
+
+
+FUSED_CASES = [c for c in CASES if c[2][0] % 64 == 0 and len(c[0]) >= 3]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES, ids=[f"{c[0]}-{c[1]}-{c[4]}" for c in FUSED_CASES])
+def test_fused_adjoint_pipeline_vs_oracle(S, case, monkeypatch):
+    """The opt-in fused adjoint (march along the slowest axis + warp-level contraction of dimension 1,
+    SG_ADJ_FUSED=1) against the C oracle, including tiles with more than 32 control indices."""
+    from gpu_helpers import make_grid, oracle_adjoint
+    n_cp, deg, n_s, nout, ft, mdo, nurbs = case
+    grid, cp, w, rng = make_grid(n_cp, deg, n_s, nout, ft, mdo=0, seed=21)
+    e = np.asfortranarray(rng.random(tuple(n_s) + (nout,)).astype(cp.dtype))
+    g = torch.full_like(grid.control_points.obtain(), -3.0)
+    monkeypatch.setenv("SG_ADJ_FUSED", "1")
+    S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g)
+    assert S.last_variant() == "adjoint_fused_j1"
+    gref = oracle_adjoint(grid, e)
+    assert rel_err(S.to_numpy(g), gref) <= _tol(ft)
+    assert max_rel_err(S.to_numpy(g), gref) <= 10 * _tol(ft)
 
 
 def test_evaluate_with_raw_and_reshaped_arrays(S):
