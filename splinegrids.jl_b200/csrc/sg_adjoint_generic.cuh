@@ -29,6 +29,10 @@ __global__ void sg_adjoint_prep_kernel(const __grid_constant__ SgGridArgs<T> a, 
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t j = tid; j + 1 < n; j += stride)
         if (idx[j] > idx[j + 1]) hdr->nonmonotone = 1;
+    if (tid == 0) {
+        hdr->span_first[d] = idx[0];
+        hdr->span_last[d] = idx[n - 1];
+    }
     for (int64_t s = tid; s <= a.n_cp[d] + 1; s += stride) {
         int64_t lo = 0, hi = n;  // first j with idx[j] >= s
         while (lo < hi) {

@@ -92,7 +92,9 @@ static inline int sg_fill_grid_args(SgGridArgs<T> &a, int nin, const int64_t *n_
 struct SgAdjointHeader {
     int nonmonotone;  // set to 1 by the prep kernel if any dimension's span indices decrease
     int fused_bad;    // (unused) kept for layout stability
-    int pad[62];
+    int span_first[SG_MAX_DIMS];   // span of the first / last sample of every dimension (1-based), written by the
+    int span_last[SG_MAX_DIMS];    // prep kernel: the control indices a (slab of a) grid can touch are [first-p, last]
+    int pad[62 - 2 * SG_MAX_DIMS];
 };
 // Fused adjoint: control-index slots reserved per warp tile of TS = 32*V samples of dimension 1.  A tile
 // touches at most TS + p control indices (every sample in its own span), p <= 5 -> TS + 8 (keeps 16-byte alignment).

@@ -133,8 +133,9 @@ static void sg_run_pass_a(const SgAdjPass &ps, SgAdjPassArgs<T> &pa, T *out, T *
     if (ps.nchunks > 1) {
         constexpr int VC = sizeof(T) == 4 ? 4 : 2;
         const bool vec_ok = (ps.inner % VC == 0);
-        dim3 cgrid((unsigned)((ps.inner + 128 * VC - 1) / (128 * VC)), (unsigned)ps.c_d, (unsigned)ps.outer);
-        sg_adj_combine_kernel<T, VC><<<cgrid, 128, 0, st>>>(out, part, hdr, ps.inner, ps.c_d, ps.G, ps.nchunks, ps.P, vec_ok, path);
+        dim3 cgrid((unsigned)((ps.inner + 128 * VC - 1) / (128 * VC)), (unsigned)((ps.c_d + SG_COMBINE_ROWS - 1) / SG_COMBINE_ROWS), (unsigned)ps.outer);
+        sg_adj_combine_kernel<T, VC><<<cgrid, 128, 0, st>>>(out, part, hdr, ps.inner, ps.c_d, ps.G, ps.nchunks, ps.P, vec_ok, path,
+                                                            pa.dim, pa.restrict_spans, pa.last_dim, pa.last_P, pa.last_div, pa.last_c);
         g_sg_launches.fetch_add(1);
     }
 }
@@ -159,6 +160,14 @@ static int sg_run_multipass(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T>
         pa.X = X; pa.Y = part; pa.table = a.table[ps.d]; pa.index = a.index[ps.d]; pa.span_start = ss.start[ps.d];
         pa.hdr = hdr; pa.inner = ps.inner; pa.n_d = ps.n_d; pa.c_d = ps.c_d; pa.G = ps.G; pa.nchunks = ps.nchunks;
         pa.path = path;
+        pa.dim = ps.d;
+        pa.last_dim = -1;
+        pa.restrict_spans = (k == 0 && a.nin >= 2) ? 1 : 0;   // only the slowest axis may be a slab of a sharded grid
+        if (k > 0) {   // outer = c_{d+1} * ... * c_D * nout: the last dimension's control index is (r / last_div) % c_D
+            pa.last_dim = a.nin - 1; pa.last_P = a.degree[a.nin - 1]; pa.last_c = a.n_cp[a.nin - 1];
+            pa.last_div = 1;
+            for (int e = ps.d + 1; e < a.nin - 1; ++e) pa.last_div *= a.n_cp[e];
+        }
         const bool rat_here = rational && k == 0;   // nin == 2: the first pass marches dim 2 over columns of dim 1
         if (rat_here) { pa.weights = weights; pa.table1 = a.table[0]; pa.index1 = a.index[0]; pa.c1 = a.n_cp[0]; }
         sg_run_pass_a<T>(ps, pa, out, part, rat_here, path, hdr, st);
@@ -167,13 +176,20 @@ static int sg_run_multipass(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T>
     // pass B: first dimension
     const int64_t outerB = a.cp_total / a.n_cp[0] * a.nout;
     const int64_t avg_range = (int64_t)(a.degree[0] + 1) * a.n_samples[0] / a.n_cp[0];
+    int b_last_dim = -1, b_last_P = 0;
+    int64_t b_last_div = 1, b_last_c = 1;
+    if (a.nin >= 2) {
+        b_last_dim = a.nin - 1; b_last_P = a.degree[a.nin - 1]; b_last_c = a.n_cp[a.nin - 1];
+        for (int e = 1; e < a.nin - 1; ++e) b_last_div *= a.n_cp[e];
+    }
     auto launch_b = [&](auto lanes_tag, auto rat_tag) {
         constexpr int L = decltype(lanes_tag)::value;
         constexpr bool R = decltype(rat_tag)::value;
         const unsigned gy = (unsigned)std::min<int64_t>(outerB, 32768);
         dim3 bgrid(sg_blocks(a.n_cp[0], 256 / L), gy, (unsigned)((outerB + gy - 1) / gy));
         sg_adj_first_dim_kernel<T, L, R><<<bgrid, 256, 0, st>>>(cp, X, a.table[0], a.index[0], ss.start[0], hdr, a.n_samples[0],
-                                                                a.n_cp[0], outerB, a.degree[0], weights, a.cp_total, path);
+                                                                a.n_cp[0], outerB, a.degree[0], weights, a.cp_total, path,
+                                                                b_last_dim, b_last_P, b_last_div, b_last_c);
     };
     if (avg_range >= 64) {
         if (rational) launch_b(std::integral_constant<int, 32>{}, std::true_type{});
@@ -185,10 +201,12 @@ static int sg_run_multipass(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T>
         if (rgrid.y > 65535) return SG_ERR_UNSUPPORTED;
         if (rational)
             sg_adj_first_dim_rows_kernel<T, 20, true><<<rgrid, 128, 0, st>>>(cp, X, a.table[0], a.index[0], ss.start[0], hdr, a.n_samples[0],
-                                                                            a.n_cp[0], outerB, a.degree[0], rpb, weights, a.cp_total, path);
+                                                                            a.n_cp[0], outerB, a.degree[0], rpb, weights, a.cp_total, path,
+                                                                            b_last_dim, b_last_P, b_last_div, b_last_c);
         else
             sg_adj_first_dim_rows_kernel<T, 20, false><<<rgrid, 128, 0, st>>>(cp, X, a.table[0], a.index[0], ss.start[0], hdr, a.n_samples[0],
-                                                                             a.n_cp[0], outerB, a.degree[0], rpb, weights, a.cp_total, path);
+                                                                             a.n_cp[0], outerB, a.degree[0], rpb, weights, a.cp_total, path,
+                                                                             b_last_dim, b_last_P, b_last_div, b_last_c);
     } else {
         if (rational) launch_b(std::integral_constant<int, 8>{}, std::true_type{});
         else launch_b(std::integral_constant<int, 8>{}, std::false_type{});
@@ -283,7 +301,7 @@ static int sg_run_fused(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &ss
     T *Y = reinterpret_cast<T *>(ws + fp.y_off);
     pa.X = eval; pa.Y = Y; pa.table = a.table[D - 1]; pa.index = a.index[D - 1]; pa.span_start = ss.start[D - 1];
     pa.hdr = hdr; pa.inner = a.n_total / a.n_samples[D - 1]; pa.n_d = a.n_samples[D - 1]; pa.c_d = a.n_cp[D - 1];
-    pa.G = (int)(a.n_cp[D - 1] - a.degree[D - 1]); pa.nchunks = 1; pa.path = SG_PATH_FUSED;
+    pa.G = (int)(a.n_cp[D - 1] - a.degree[D - 1]); pa.nchunks = 1; pa.path = SG_PATH_FUSED; pa.dim = D - 1; pa.last_dim = -1;
     pa.table1 = a.table[0]; pa.index1 = a.index[0]; pa.c1 = a.n_cp[0]; pa.n1 = a.n_samples[0]; pa.P1 = a.degree[0];
     pa.tile_lo = ss.tile_lo; pa.tile_ni = ss.tile_ni; pa.n_tiles = fp.n_tiles; pa.n_slots = fp.n_slots; pa.span_start1 = ss.start[0];
     switch (a.degree[D - 1]) {
@@ -299,7 +317,7 @@ static int sg_run_fused(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &ss
         SgAdjPassArgs<T> pm{};
         pm.X = X; pm.Y = part; pm.table = a.table[ps.d]; pm.index = a.index[ps.d]; pm.span_start = ss.start[ps.d];
         pm.hdr = hdr; pm.inner = ps.inner; pm.n_d = ps.n_d; pm.c_d = ps.c_d; pm.G = ps.G; pm.nchunks = ps.nchunks;
-        pm.path = SG_PATH_FUSED; pm.tile_ni = ss.tile_ni; pm.n_tiles = fp.n_tiles; pm.n_slots = fp.n_slots;
+        pm.path = SG_PATH_FUSED; pm.dim = ps.d; pm.last_dim = -1; pm.tile_ni = ss.tile_ni; pm.n_tiles = fp.n_tiles; pm.n_slots = fp.n_slots;
         sg_run_pass_a<T>(ps, pm, out, part, false, SG_PATH_FUSED, hdr, st);
         X = out;
     }

@@ -32,6 +32,14 @@ __device__ __forceinline__ bool sg_adj_path_active(const SgAdjointHeader *h, int
     (void)path;
     return h->nonmonotone == 0;
 }
+// Is control index i_D (1-based) of the last dimension inside the support [first_span - p, last_span]?
+__device__ __forceinline__ bool sg_adj_row_in_support(const SgAdjointHeader *h, int last_dim, int last_P, int64_t last_div,
+                                                      int64_t last_c, int64_t r)
+{
+    if (last_dim < 0) return true;
+    const int64_t iD = (r / last_div) % last_c + 1;
+    return iD >= h->span_first[last_dim] - last_P && iD <= h->span_last[last_dim];
+}
 
 template <typename T>
 struct SgAdjPassArgs {
@@ -49,6 +57,13 @@ struct SgAdjPassArgs {
     const int32_t *index1;
     int64_t c1;
     int path;                   // SG_PATH_*
+    int dim;                    // 0-based dimension contracted by this pass (selects hdr->span_first/last)
+    int restrict_spans;         // 1 (last dimension only): visit just the spans that hold samples; rows outside stay unwritten
+    // passes over dims below the last one: the outer index r contains the LAST dimension's control index,
+    // i_D = (r / last_div) % last_c; rows outside the support of this (slab of the) grid are skipped.
+    int last_dim;               // -1: no skipping
+    int last_P;
+    int64_t last_div, last_c;
     // passes that follow the fused first pass: the contiguous axis is [n_slots][n_tiles]; slots >= tile_ni[tile]
     // were never written and are skipped
     const int32_t *tile_ni;
@@ -91,8 +106,13 @@ __global__ void __launch_bounds__(128) sg_adj_march_kernel(const __grid_constant
     const int64_t q0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
     const int c = blockIdx.y;
     const int64_t r = (int64_t)blockIdx.z * NT;                       // first of this thread's NT outer channels
-    const int s_lo = P + 1 + c * a.G;                                  // first span of this chunk (1-based)
-    const int s_hi = (int)min((int64_t)s_lo + a.G, a.c_d + 1);         // one past the last span
+    if (!sg_adj_row_in_support(a.hdr, a.last_dim, a.last_P, a.last_div, a.last_c, r)) return;   // block-uniform
+    const int s_lo0 = P + 1 + c * a.G;                                 // first span of this chunk (1-based)
+    const int s_hi0 = (int)min((int64_t)s_lo0 + a.G, a.c_d + 1);       // one past the last span
+    // only the spans that actually hold samples (a slab of a sharded grid covers a sub-range)
+    const int s_lo = a.restrict_spans ? max(s_lo0, a.hdr->span_first[a.dim]) : s_lo0;
+    const int s_hi = a.restrict_spans ? min(s_hi0, a.hdr->span_last[a.dim] + 1) : s_hi0;
+    if (s_lo >= s_hi) return;                                          // block-uniform
     const int64_t j_lo = a.span_start[s_lo], j_hi = a.span_start[s_hi];
     bool active = q0 < a.inner;
     if (a.tile_ni != nullptr && active)   // slot axis after the fused first pass: skip never-written slots
@@ -101,7 +121,7 @@ __global__ void __launch_bounds__(128) sg_adj_march_kernel(const __grid_constant
     const int64_t inner = a.inner;
 
     const T *__restrict__ xp = a.X + q0 + inner * (j_lo + a.n_d * r);
-    T *__restrict__ yp = a.Y + q0 + inner * ((int64_t)rows * (c + (int64_t)a.nchunks * r));   // oldest live row
+    T *__restrict__ yp = a.Y + q0 + inner * ((int64_t)rows * (c + (int64_t)a.nchunks * r) + (s_lo - s_lo0));   // oldest live row
     const int64_t x_ch = inner * a.n_d;                                // channel strides
     const int64_t y_ch = inner * (int64_t)rows * a.nchunks;
 
@@ -259,42 +279,54 @@ __global__ void __launch_bounds__(128) sg_adj_march_kernel(const __grid_constant
 }
 
 // combine chunk partials: Y[q, i, r] = sum_c P[q, i - (c*G + 1), c, r]   (i 1-based control index).
-// grid = (inner / (128*V), c_d, outer): no integer division in the kernel, vector loads/stores.
+// grid = (inner / (128*V), ceil(c_d / SG_COMBINE_ROWS), outer): no integer division, vector loads/stores.
+#define SG_COMBINE_ROWS 8
 template <typename T, int V>
 __global__ void __launch_bounds__(128) sg_adj_combine_kernel(T *__restrict__ Y, const T *__restrict__ Pp, const SgAdjointHeader *hdr,
-                                                             int64_t inner, int64_t c_d, int G, int nchunks, int P, bool vec_ok, int path)
+                                                             int64_t inner, int64_t c_d, int G, int nchunks, int P, bool vec_ok, int path,
+                                                             int dim, int restrict_spans, int last_dim, int last_P, int64_t last_div, int64_t last_c)
 {
     if (!sg_adj_path_active(hdr, path)) return;
     const int64_t q0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
     if (q0 >= inner) return;
-    const int64_t i = (int64_t)blockIdx.y + 1;
     const int64_t r = blockIdx.z;
+    if (!sg_adj_row_in_support(hdr, last_dim, last_P, last_div, last_c, r)) return;
+    const int sf = restrict_spans ? hdr->span_first[dim] : P + 1;
+    const int sl = restrict_spans ? hdr->span_last[dim] : (int)c_d;
     const int nv = (int)min((int64_t)V, inner - q0);
     const bool vec = vec_ok && nv == V;
     const int rows = G + P;
-    // chunk c holds rows i in [c*G + 1, c*G + G + P]
-    int64_t c_hi = (i - 1) / G;
-    if (c_hi > nchunks - 1) c_hi = nchunks - 1;
-    int64_t c_lo = (i - P - 1 >= 0) ? (i - P - 1) / G : 0;
-    if (c_lo > 0 && (c_lo - 1) * G + G + P >= i) --c_lo;
-    T acc[V];
+    const int64_t i_end = min((int64_t)(blockIdx.y + 1) * SG_COMBINE_ROWS, c_d);
+    for (int64_t i = (int64_t)blockIdx.y * SG_COMBINE_ROWS + 1; i <= i_end; ++i) {
+        if (i < sf - P || i > sl) continue;                             // row not touched by any sample: stays unread
+        // chunk c holds rows i in [c*G + 1, c*G + G + P]
+        int64_t c_hi = (i - 1) / G;
+        if (c_hi > nchunks - 1) c_hi = nchunks - 1;
+        int64_t c_lo = (i - P - 1 >= 0) ? (i - P - 1) / G : 0;
+        if (c_lo > 0 && (c_lo - 1) * G + G + P >= i) --c_lo;
+        T acc[V];
 #pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = T(0);
-    for (int64_t c = c_lo; c <= c_hi; ++c) {
-        const int64_t local = i - (c * G + 1);
-        if (local < 0 || local >= rows) continue;
-        const T *__restrict__ src = Pp + q0 + inner * (local + (int64_t)rows * (c + (int64_t)nchunks * r));
-        if (vec) {
-            typename SgVecT<T, V>::type pk = __ldcs(reinterpret_cast<const typename SgVecT<T, V>::type *>(src));
-            const T *pq = reinterpret_cast<const T *>(&pk);
+        for (int v = 0; v < V; ++v) acc[v] = T(0);
+        for (int64_t c = c_lo; c <= c_hi; ++c) {
+            const int64_t local = i - (c * G + 1);
+            if (local < 0 || local >= rows) continue;
+            // rows a chunk really wrote: spans [max(s_lo0, sf), min(s_hi0, sl+1)) -> control rows [lo-P, hi-1]
+            const int64_t cs_lo = max((int64_t)(P + 1 + c * G), (int64_t)sf);
+            const int64_t cs_hi = min(min((int64_t)(P + 1 + c * G + G), c_d + 1), (int64_t)sl + 1);
+            if (cs_lo >= cs_hi || i < cs_lo - P || i > cs_hi - 1) continue;
+            const T *__restrict__ src = Pp + q0 + inner * (local + (int64_t)rows * (c + (int64_t)nchunks * r));
+            if (vec) {
+                T x[V];
+                sg_load_vec<T, V>(src, x);
 #pragma unroll
-            for (int v = 0; v < V; ++v) acc[v] += pq[v];
-        } else {
+                for (int v = 0; v < V; ++v) acc[v] += x[v];
+            } else {
 #pragma unroll
-            for (int v = 0; v < V; ++v) if (v < nv) acc[v] += __ldcs(src + v);
+                for (int v = 0; v < V; ++v) if (v < nv) acc[v] += __ldcs(src + v);
+            }
         }
+        sg_store_vec<T, V>(Y + q0 + inner * ((i - 1) + c_d * r), acc, vec, nv);
     }
-    sg_store_vec<T, V>(Y + q0 + inner * ((i - 1) + c_d * r), acc, vec, nv);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -306,9 +338,12 @@ template <typename T, int L, bool RATIONAL>
 __global__ void __launch_bounds__(256) sg_adj_first_dim_kernel(T *__restrict__ cp, const T *__restrict__ X, const T *__restrict__ table,
                                                                const int32_t *__restrict__ index, const int32_t *__restrict__ span_start,
                                                                const SgAdjointHeader *hdr, int64_t n1, int64_t c1, int64_t outer, int P,
-                                                               const T *__restrict__ weights, int64_t cp_total, int path)
+                                                               const T *__restrict__ weights, int64_t cp_total, int path,
+                                                               int last_dim, int last_P, int64_t last_div, int64_t last_c)
 {
     if (!sg_adj_path_active(hdr, path)) return;
+    if (!sg_adj_row_in_support(hdr, last_dim, last_P, last_div, last_c,
+                               (int64_t)blockIdx.y + (int64_t)gridDim.y * blockIdx.z)) return;   // cp stays zero (memset)
     // grid = (ceil(c1 / (256/L)), outer split over y and z): no integer division
     const int64_t i0 = (int64_t)blockIdx.x * (256 / L) + threadIdx.x / L;   // 0-based control index
     const int64_t r = (int64_t)blockIdx.y + (int64_t)gridDim.y * blockIdx.z;
@@ -345,7 +380,8 @@ template <typename T, int RMAX, bool RATIONAL>
 __global__ void __launch_bounds__(128) sg_adj_first_dim_rows_kernel(T *__restrict__ cp, const T *__restrict__ X, const T *__restrict__ table,
                                                                     const int32_t *__restrict__ index, const int32_t *__restrict__ span_start,
                                                                     const SgAdjointHeader *hdr, int64_t n1, int64_t c1, int64_t outer, int P,
-                                                                    int rows_per_block, const T *__restrict__ weights, int64_t cp_total, int path)
+                                                                    int rows_per_block, const T *__restrict__ weights, int64_t cp_total, int path,
+                                                                    int last_dim, int last_P, int64_t last_div, int64_t last_c)
 {
     if (!sg_adj_path_active(hdr, path)) return;
     const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // 0-based control index
@@ -359,6 +395,7 @@ __global__ void __launch_bounds__(128) sg_adj_first_dim_rows_kernel(T *__restric
     const int64_t r_hi = min(r_lo + rows_per_block, outer);
     if (len > RMAX) {   // long range: direct look-ups
         for (int64_t r = r_lo; r < r_hi; ++r) {
+            if (!sg_adj_row_in_support(hdr, last_dim, last_P, last_div, last_c, r)) continue;
             T acc = T(0);
             for (int64_t j = lo; j < hi; ++j) {
                 const int k = (int)(i - sg_ldg(index + j) + P);
@@ -383,7 +420,10 @@ __global__ void __launch_bounds__(128) sg_adj_first_dim_rows_kernel(T *__restric
     const int64_t jmax = n1 - 1;
     int64_t r = r_lo;
     for (; r + 1 < r_hi; r += 2) {   // two rows per iteration for ILP
-        const T *__restrict__ x0 = X + n1 * r, *__restrict__ x1 = x0 + n1;
+        const bool in0 = sg_adj_row_in_support(hdr, last_dim, last_P, last_div, last_c, r);
+        const bool in1 = sg_adj_row_in_support(hdr, last_dim, last_P, last_div, last_c, r + 1);
+        if (!in0 && !in1) continue;                                     // outside the slab's support: cp stays zero
+        const T *__restrict__ x0 = X + n1 * (in0 ? r : r + 1), *__restrict__ x1 = X + n1 * (in1 ? r + 1 : r);
         T a0 = T(0), a1 = T(0);
 #pragma unroll
         for (int t = 0; t < RMAX; ++t) {
@@ -395,10 +435,10 @@ __global__ void __launch_bounds__(128) sg_adj_first_dim_rows_kernel(T *__restric
         }
         const int64_t lin = i0 + c1 * r;
         if (RATIONAL) { a0 *= sg_ldg(weights + lin % cp_total); a1 *= sg_ldg(weights + (lin + c1) % cp_total); }
-        cp[lin] = a0;
-        cp[lin + c1] = a1;
+        if (in0) cp[lin] = a0;
+        if (in1) cp[lin + c1] = a1;
     }
-    if (r < r_hi) {
+    if (r < r_hi && sg_adj_row_in_support(hdr, last_dim, last_P, last_div, last_c, r)) {
         const T *__restrict__ x0 = X + n1 * r;
         T a0 = T(0);
 #pragma unroll

@@ -62,6 +62,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--ops", default="evaluate,adjoint")
     ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--slab", type=int, default=1, help="time the middle slab of an N-way slab-sharded grid (1 GPU)")
     args = ap.parse_args()
     S = entry.load_package()
     S.set_synchronous(False)
@@ -73,7 +74,10 @@ def main():
         rng = np.random.default_rng(1)
         dims = tuple(S.SplineDimension(c, p, n, float_type=cfg["ft"], max_derivative_order=cfg.get("mdo", 0))
                      for c, p, n in zip(cfg["n_cp"], cfg["deg"], cfg["n_s"]))
-        grid = S.NURBSGrid(dims, cfg["nout"]) if cfg.get("nurbs") else S.SplineGrid(dims, cfg["nout"])
+        if args.slab > 1:
+            grid = S.SlabShardedGrid(dims, cfg["nout"], args.slab // 2, args.slab, nurbs=bool(cfg.get("nurbs"))).local
+        else:
+            grid = S.NURBSGrid(dims, cfg["nout"]) if cfg.get("nurbs") else S.SplineGrid(dims, cfg["nout"])
         dt = torch.float32 if cfg["ft"] == "Float32" else torch.float64
         grid.control_points.obtain().copy_(torch.rand(grid.control_points.shape, dtype=dt, device="cuda"))
         if cfg.get("nurbs"):
@@ -83,6 +87,10 @@ def main():
         g_out = torch.zeros_like(grid.control_points.obtain())
         nbytes = algorithmic_bytes(cfg)
         values = int(np.prod(cfg["n_s"])) * cfg["nout"]
+        if args.slab > 1:
+            cfg_l = dict(cfg, n_s=tuple(grid.eval.shape[:-1]))
+            nbytes = algorithmic_bytes(cfg_l)
+            values = int(np.prod(cfg_l["n_s"])) * cfg["nout"]
         for pol in [int(p) for p in args.policies.split(",")]:
             S.set_kernel_policy(pol)
             for op in args.ops.split(","):
@@ -94,7 +102,7 @@ def main():
                 med, best = time_op(fn, 2 if big else args.iters, 1 if big else args.warmup,
                                     flush if (nbytes < 200e6 and args.batch == 1) else None,
                                     1 if big else args.batch)
-                print(json.dumps({"config": name, "op": op, "policy": pol, "variant": S.last_variant(),
+                print(json.dumps({"config": name + (f"/slab{args.slab}" if args.slab > 1 else ""), "op": op, "policy": pol, "variant": S.last_variant(),
                                   "ms_median": round(med, 4), "ms_min": round(best, 4),
                                   "values_per_s": values / (med * 1e-3), "alg_GBs": nbytes / (med * 1e-3) / 1e9,
                                   "frac_of_measured_hbm": nbytes / (med * 1e-3) / 1e9 / hbm}), flush=True)
