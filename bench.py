@@ -200,7 +200,7 @@ def main_gpu(args):
     S.set_synchronous(False)                       # the benchmark synchronises once per timed region
     gdims = tuple(S.SplineDimension(c, p, n, float_type=w["float_type"])
                   for c, p, n in zip(w["n_cp"], w["degree"], w["n_samples"]))
-    sh = S.SlabShardedGrid(gdims, w["nout"], rank, world)
+    sh = S.SlabShardedGrid(gdims, w["nout"], rank, world, peer_exchange=(world > 1 and not args.nccl_allreduce))
     grid = sh.local
     n_local = tuple(grid.eval.shape[:-1])
     gen = torch.Generator(device=dev)
@@ -223,6 +223,17 @@ def main_gpu(args):
         sh.evaluate_adjoint_(eval=e_in, control_points=grad)          # local adjoint + NCCL all-reduce (N > 1)
 
     values_per_step = 2 * int(np.prod(w["n_samples"])) * w["nout"]      # whole job, both ops
+    exchange_check = None
+    if world > 1 and args.check:
+        # the exchanged gradient must equal the all-reduced local partial gradients
+        S.evaluate_adjoint_(grid, eval=e_in, control_points=grad)
+        ref = grad.clone()
+        S.allreduce_gradient_(ref)
+        sh.evaluate_adjoint_(eval=e_in, control_points=grad)
+        torch.cuda.synchronize()
+        err = float((grad - ref).norm() / ref.norm())
+        exchange_check = {"kind": sh.exchange_kind, "rel_err_vs_allreduce": err}
+        assert err < 1e-12, f"gradient exchange mismatch: {err}"
 
     # ---- kernel-only timing: K steps between two events, max over ranks ---------------------------
     for _ in range(args.warmup):
@@ -338,6 +349,7 @@ def main_gpu(args):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": w["name"], "step": "evaluate! + evaluate_adjoint! (+ NCCL all-reduce of the gradient for N>1)",
                            "sharding": f"sample grid in {world} slab(s) along axis 3, control points replicated",
+                           "gradient_exchange": sh.exchange_kind, "exchange_check": exchange_check,
                            "l2": "inputs/outputs (1.07 GB per op) exceed the 126 MB L2; no flush needed"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "ops": ops,
                 "cpu_baseline": cpu}
@@ -356,6 +368,8 @@ def main():
     ap.add_argument("--cpu-planes", type=int, default=32, help="slab thickness of the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-allreduce", action="store_true", help="N>1: use the NCCL all-reduce instead of the peer-memory exchange")
+    ap.add_argument("--check", action="store_true", help="N>1: verify the exchanged gradient against an NCCL all-reduce")
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/)")
     args = ap.parse_args()

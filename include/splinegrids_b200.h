@@ -187,6 +187,25 @@ int sg_comm_destroy(sg_comm *comm);
 int sg_allreduce_sum_f32(float *buf, int64_t count, sg_comm *comm, void *stream);
 int sg_allreduce_sum_f64(double *buf, int64_t count, sg_comm *comm, void *stream);
 
+/* ---- multi-GPU: gradient exchange over NVLink peer memory (new; replaces the all-reduce when the ranks'
+ * staging buffers are peer-mapped, e.g. CUDA IPC / symmetric memory) ------------------------------------
+ * A slab's partial gradient is non-zero only on control planes [k0, k0+np) of the slowest control axis.
+ * sg_exchange_push:   copy those planes of `grad` (plane_elems, c_last, nout) into slot `my_rank` of EVERY
+ *                     rank's staging buffer with peer-to-peer stores; peer_stage is a HOST array of `world`
+ *                     device pointers (this rank's own buffer included).  Staging layout per rank:
+ *                     [world][nout][max_planes][plane_elems].
+ * (all ranks then synchronise on the stream -- barrier supplied by the host framework --)
+ * sg_exchange_reduce: grad[:, k, o] = sum over ranks r whose support covers plane k of stage[r][o][k-k0_r][:],
+ *                     summed in rank order (deterministic); k0s / nps are HOST arrays of length world. */
+int sg_exchange_push_f32(const float *grad, void *const *peer_stage, int world, int my_rank, int64_t plane_elems,
+                         int64_t c_last, int nout, int64_t k0, int64_t np, int64_t max_planes, void *stream);
+int sg_exchange_push_f64(const double *grad, void *const *peer_stage, int world, int my_rank, int64_t plane_elems,
+                         int64_t c_last, int nout, int64_t k0, int64_t np, int64_t max_planes, void *stream);
+int sg_exchange_reduce_f32(float *grad, const float *stage, int world, const int64_t *k0s, const int64_t *nps,
+                           int64_t plane_elems, int64_t c_last, int nout, int64_t max_planes, void *stream);
+int sg_exchange_reduce_f64(double *grad, const double *stage, int world, const int64_t *k0s, const int64_t *nps,
+                           int64_t plane_elems, int64_t c_last, int nout, int64_t max_planes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,70 @@ def allreduce_gradient_(control_points: torch.Tensor, group=None) -> torch.Tenso
     return control_points
 
 
+class PeerGradientExchange:
+    """Gradient exchange over NVLink peer memory (replaces the all-reduce).
+
+    A slab's partial gradient is non-zero only on the control planes its samples touch.  Every rank pushes
+    those planes into its slot of every peer's staging buffer with peer-to-peer stores
+    (``sg_exchange_push``), the ranks meet at a stream-ordered barrier, and each rank sums the few slots
+    that cover each plane (``sg_exchange_reduce``, rank order -> deterministic).  The staging buffers are
+    ``torch.distributed._symmetric_memory`` allocations (plumbing); the kernels are ours.  Two staging buffers
+    alternate so one barrier per exchange suffices.
+    """
+
+    def __init__(self, global_dims: Sequence[SplineDimension], Nout: int, rank: int, world_size: int, group=None):
+        import numpy as np
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        last = global_dims[-1]
+        idx = last.sample_indices.cpu().numpy()
+        p = last.degree
+        self.k0, self.np_ = [], []
+        for r in range(world_size):
+            lo, hi = slab_bounds(last.n_sample_points, world_size, r)
+            k0 = int(idx[lo]) - p - 1
+            self.k0.append(k0)
+            self.np_.append(int(idx[hi - 1]) - k0)
+        self.rank, self.world = rank, world_size
+        self.c_last = last.n_basis_functions
+        self.plane_elems = int(np.prod([sd.n_basis_functions for sd in global_dims[:-1]])) if len(global_dims) > 1 else 1
+        self.nout = int(Nout)
+        self.max_planes = max(self.np_)
+        self.dtype, self.device = last.dtype, last.device
+        slot = self.nout * self.max_planes * self.plane_elems
+        grp = dist.group.WORLD if group is None else group
+        self.stage, self.hdl, self.peer_ptrs = [], [], []
+        for _ in range(2):
+            t = symm_mem.empty(world_size * slot, dtype=self.dtype, device=self.device)
+            h = symm_mem.rendezvous(t, grp)
+            self.stage.append(t)
+            self.hdl.append(h)
+            self.peer_ptrs.append((_lib.C.c_void_p * world_size)(*[int(x) for x in h.buffer_ptrs]))
+        self._k0s = _lib.i64_array(self.k0)
+        self._nps = _lib.i64_array(self.np_)
+        self.step = 0
+
+    def exchange_(self, grad: torch.Tensor) -> torch.Tensor:
+        from . import _lib
+        C = _lib.C
+        b = self.step & 1
+        self.step += 1
+        suf = _lib.suffix(self.dtype)
+        st = _lib.stream_ptr(self.device)
+        lib = _lib.lib()
+        _lib.check(getattr(lib, "sg_exchange_push_" + suf)(
+            _lib.ptr(grad), self.peer_ptrs[b], C.c_int(self.world), C.c_int(self.rank), C.c_int64(self.plane_elems),
+            C.c_int64(self.c_last), C.c_int(self.nout), C.c_int64(self.k0[self.rank]), C.c_int64(self.np_[self.rank]),
+            C.c_int64(self.max_planes), st), "sg_exchange_push")
+        self.hdl[b].barrier(channel=0)                      # stream-ordered, all ranks
+        _lib.check(getattr(lib, "sg_exchange_reduce_" + suf)(
+            _lib.ptr(grad), _lib.ptr(self.stage[b]), C.c_int(self.world), self._k0s, self._nps,
+            C.c_int64(self.plane_elems), C.c_int64(self.c_last), C.c_int(self.nout), C.c_int64(self.max_planes), st),
+            "sg_exchange_reduce")
+        return grad
+
+
 class SlabShardedGrid:
     """This rank's slab of a global spline grid.
 
@@ -64,14 +128,23 @@ class SlabShardedGrid:
     """
 
     def __init__(self, global_dims: Sequence[SplineDimension], Nout: int, rank: int, world_size: int,
-                 nurbs: bool = False, group=None):
+                 nurbs: bool = False, group=None, peer_exchange: bool = False):
         self.global_dims = tuple(global_dims)
         self.rank, self.world_size, self.group = rank, world_size, group
+        self.exchange = None
+        self.exchange_kind = "none" if world_size == 1 else "nccl_allreduce"
         n_last = self.global_dims[-1].n_sample_points
         assert n_last >= world_size, "fewer sample rows along the slowest axis than ranks"
         self.lo, self.hi = slab_bounds(n_last, world_size, rank)
         dims = self.global_dims[:-1] + (slice_dimension(self.global_dims[-1], self.lo, self.hi),)
         self.local: SplineGrid = NURBSGrid(dims, Nout) if nurbs else SplineGrid(dims, Nout)
+        if peer_exchange and world_size > 1:
+            try:
+                self.exchange = PeerGradientExchange(self.global_dims, Nout, rank, world_size, group)
+                self.exchange_kind = "peer_memory_push_reduce"
+            except Exception as e:   # symmetric memory unavailable: keep the NCCL all-reduce
+                import warnings
+                warnings.warn(f"peer-memory gradient exchange unavailable ({e!r}); using the NCCL all-reduce")
 
     @property
     def global_sample_grid_size(self) -> Tuple[int, ...]:
@@ -86,4 +159,7 @@ class SlabShardedGrid:
         full gradient, exactly what the single-device call produces (up to summation order)."""
         evaluate_adjoint_(self.local, control_points=control_points, **kw)
         cp = obtain(self.local.control_points if control_points is None else control_points)
-        allreduce_gradient_(cp, self.group)
+        if self.exchange is not None:
+            self.exchange.exchange_(cp)
+        else:
+            allreduce_gradient_(cp, self.group)
