@@ -49,9 +49,16 @@ static SgAdjPlan sg_adjoint_plan(int nin, const int64_t *n_samples, const int64_
         ps.outer = outer;
         ps.P = degree[d];
         const int64_t nspans = ps.c_d - ps.P;
-        const int64_t threads = ((ps.inner + V - 1) / V) * outer;
+        // columns that will really be active: a slab of a sharded grid touches at most n_D + p_D of the c_D control
+        // planes of the slowest axis (the kernels skip the others on device)
+        int64_t outer_est = outer;
+        if (d < nin - 1) {
+            const int64_t cD = n_cp[nin - 1], actD = std::min<int64_t>(cD, n_samples[nin - 1] + degree[nin - 1]);
+            outer_est = outer / cD * actD;
+        }
+        const int64_t threads = ((ps.inner + V - 1) / V) * outer_est;
         int64_t nchunks = 1;
-        if (threads < 65536) nchunks = std::min<int64_t>(nspans, (148 * 8 * 128 + threads - 1) / threads);
+        if (threads < 24576) nchunks = std::min<int64_t>(nspans, (148 * 8 * 128 + threads - 1) / threads);
         const int forced = sg_env_int("SG_ADJ_CHUNKS", 0);
         if (forced > 0) nchunks = std::min<int64_t>(nspans, forced);
         ps.G = (int)((nspans + nchunks - 1) / nchunks);

@@ -24,15 +24,48 @@ static bool sg_uniform_degree(const int *deg, int nin, int &p)
 }
 
 // number of marching chunks so that the grid has a few waves of CTAs on 148 SMs
-static int sg_pick_chunk(int64_t n_march, int64_t col_tiles, int min_chunk, int max_chunk, int env_override)
+static int sg_pick_chunk(int64_t n_march, int64_t col_tiles, int min_chunk, int max_chunk, int env_override,
+                         int64_t target_ctas = 148 * 8)
 {
     if (env_override > 0) return (int)std::min<int64_t>(std::max(env_override, 1), std::min<int64_t>(n_march, max_chunk));
-    const int64_t target_ctas = 148 * 8;
     int64_t nchunks = (target_ctas + col_tiles - 1) / col_tiles;
     nchunks = std::max<int64_t>(1, std::min<int64_t>(nchunks, (n_march + min_chunk - 1) / min_chunk));
     int64_t chunk = (n_march + nchunks - 1) / nchunks;
+    chunk = (chunk + 7) / 8 * 8;                       // multiples of 8 steps: fewer ragged tail chunks
     chunk = std::min<int64_t>(std::max<int64_t>(chunk, 1), max_chunk);
     return (int)chunk;
+}
+
+// ---- TMA tensor map for the control points (c1, c2, c3, nout), box (B1, B2, B3, 1) ------------------------
+typedef CUresult (*SgEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static SgEncodeTiledFn sg_get_encoder()
+{
+    static SgEncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<SgEncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+template <typename T>
+static bool sg_make_cp_tensor_map(CUtensorMap &tm, const T *cp, const SgGridArgs<T> &a)
+{
+    SgEncodeTiledFn enc = sg_get_encoder();
+    if (!enc) return false;
+    const cuuint64_t c1 = a.n_cp[0], c2 = a.n_cp[1], c3 = a.n_cp[2];
+    if ((c1 * sizeof(T)) % 16 != 0 || reinterpret_cast<uintptr_t>(cp) % 16 != 0) return false;   // TMA stride/base alignment
+    cuuint64_t dims[4] = {c1, c2, c3, (cuuint64_t)a.nout};
+    cuuint64_t strides[3] = {c1 * sizeof(T), c1 * c2 * sizeof(T), c1 * c2 * c3 * sizeof(T)};   // bytes, dims 1..3
+    cuuint32_t box[4] = {SG_TMA_B1, SG_TMA_B2, SG_TMA_B3, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    return enc(&tm, dt, 4, const_cast<T *>(cp), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <typename T, int P, int V1, int V2, int TY>
@@ -40,13 +73,27 @@ static int sg_launch_eval3d(T *eval, const SgGridArgs<T> &a, const T *cp, cudaSt
 {
     const int64_t gx = (a.n_samples[0] + 32 * V1 - 1) / (32 * V1);
     const int64_t gy = (a.n_samples[1] + TY * V2 - 1) / (TY * V2);
-    const int chunk = sg_pick_chunk(a.n_samples[2], gx * gy, 32, 1024, sg_env_int("SG_CHUNK3D", 0));
+    // (the TMA variant stages at most SG_TMA_B3 control planes per CTA: a finer cut of the marching axis suits it)
+    const int chunk = sg_pick_chunk(a.n_samples[2], gx * gy, 32, 1024, sg_env_int("SG_CHUNK3D", 0), 148 * 14);
     const int64_t gz = (a.n_samples[2] + chunk - 1) / chunk;
     if (gy > 65535 || gz > 65535) return SG_ERR_UNSUPPORTED;
     const bool vec_ok = (reinterpret_cast<uintptr_t>(eval) % 16 == 0) && (a.n_samples[0] % V1 == 0);
-    const size_t smem = (size_t)chunk * ((P + 1) * sizeof(T) + sizeof(int));
+    const size_t smem_march = (((size_t)chunk * ((P + 1) * sizeof(T) + sizeof(int)) + 15) & ~(size_t)15) + 16;
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gz), block(32, TY);
-    sg_eval3d_march_kernel<T, P, V1, V2, TY><<<grid, block, smem, st>>>(eval, a, cp, chunk, a.nout, vec_ok);
+    CUtensorMap tm{};
+    if (sg_env_int("SG_EVAL_TMA", 1) && sg_make_cp_tensor_map<T>(tm, cp, a)) {
+        // control-point window staged by one TMA bulk tensor copy per CTA
+        const size_t smem = sizeof(T) * SG_TMA_B1 * SG_TMA_B2 * SG_TMA_B3 + smem_march;
+        auto kern = sg_eval3d_march_kernel<T, P, V1, V2, TY, true>;
+        SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        if (smem <= 160 * 1024) {
+            kern<<<grid, block, smem, st>>>(eval, a, cp, chunk, a.nout, vec_ok, tm);
+            g_sg_last_variant = "evaluate_march3d_tma";
+            SG_AFTER_LAUNCH();
+            return SG_OK;
+        }
+    }
+    sg_eval3d_march_kernel<T, P, V1, V2, TY, false><<<grid, block, smem_march, st>>>(eval, a, cp, chunk, a.nout, vec_ok, tm);
     g_sg_last_variant = "evaluate_march3d";
     SG_AFTER_LAUNCH();
     return SG_OK;

@@ -17,7 +17,44 @@
 // (fewer samples than spans, unsorted samples) that thread alone takes a slow, direct path, so the
 // kernels are correct for ANY span indices.  Reference semantics: src/spline_grid.jl:119-183.
 #pragma once
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
+
 #include "sg_common.cuh"
+
+// ---- TMA / mbarrier primitives (PTX; sm_90+ async proxy, used here on sm_100a) -----------------------
+#define SG_TMA_B1 24   // control-tile box: dimension 1 (elements)
+#define SG_TMA_B2 12   //                   dimension 2
+#define SG_TMA_B3 32   //                   planes of the marching dimension
+__device__ __forceinline__ uint32_t sg_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sg_mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sg_smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // make the init visible to the async proxy
+}
+__device__ __forceinline__ void sg_mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sg_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sg_mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SG_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SG_DONE_%=;\n"
+        "bra SG_WAIT_%=;\n"
+        "SG_DONE_%=:\n"
+        "}\n" ::"r"(sg_smem_u32(bar)), "r"(parity) : "memory");
+}
+// 4-D tiled bulk tensor load global -> shared, completion signalled on the mbarrier (cp.async.bulk.tensor = TMA)
+__device__ __forceinline__ void sg_tma_load_4d(void *dst, const CUtensorMap *tmap, int c0, int c1, int c2, int c3, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(sg_smem_u32(dst)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(sg_smem_u32(bar))
+        : "memory");
+}
 
 template <typename T, int N> struct SgVecT;
 template <> struct SgVecT<float, 4> { using type = float4; };
@@ -99,15 +136,23 @@ __device__ __forceinline__ bool sg_expand_weights(const T *__restrict__ table, c
 // =============================================================================================
 // 3-D
 // =============================================================================================
-template <typename T, int P, int V1, int V2, int TY>
+// TMA = true: the CTA's whole control-point window (SG_TMA_B1 x SG_TMA_B2 control points x SG_TMA_B3 planes, a 4-D
+// tensor-map box, zero-filled out of bounds) is fetched into shared memory by ONE bulk tensor copy per output
+// channel, signalled on an mbarrier; plane contractions then read shared memory instead of L2.  Threads (or
+// planes) whose window does not fit the box transparently use the global-load path.
+template <typename T, int P, int V1, int V2, int TY, bool TMA>
 __global__ void __launch_bounds__(32 * TY) sg_eval3d_march_kernel(T *__restrict__ eval, const __grid_constant__ SgGridArgs<T> a,
-                                                                  const T *__restrict__ cp, int chunk, int o_count, bool vec_ok)
+                                                                  const T *__restrict__ cp, int chunk, int o_count, bool vec_ok,
+                                                                  const __grid_constant__ CUtensorMap tmap)
 {
     constexpr int E = 1;
     constexpr int WD = P + 1 + E;
-    extern __shared__ __align__(16) unsigned char sg_smem[];
-    T *b3s = reinterpret_cast<T *>(sg_smem);                         // [chunk][P+1]
+    extern __shared__ __align__(128) unsigned char sg_smem[];
+    constexpr size_t TILE_BYTES = TMA ? sizeof(T) * SG_TMA_B1 * SG_TMA_B2 * SG_TMA_B3 : 0;
+    T *tile = reinterpret_cast<T *>(sg_smem);                         // [B3][B2][B1] (TMA only)
+    T *b3s = reinterpret_cast<T *>(sg_smem + TILE_BYTES);             // [chunk][P+1]
     int *s3s = reinterpret_cast<int *>(b3s + (size_t)chunk * (P + 1));   // [chunk]
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(sg_smem + TILE_BYTES + (((size_t)chunk * ((P + 1) * sizeof(T) + sizeof(int)) + 15) & ~(size_t)15));
 
     const int64_t n1 = a.n_samples[0], n2 = a.n_samples[1], n3 = a.n_samples[2];
     const int64_t c1 = a.n_cp[0], c2 = a.n_cp[1];
@@ -123,8 +168,23 @@ __global__ void __launch_bounds__(32 * TY) sg_eval3d_march_kernel(T *__restrict_
 #pragma unroll
         for (int k = 0; k <= P; ++k) b3s[s * (P + 1) + k] = sg_ldg(a.table[2] + j3_lo + s + n3 * k);
     }
+    // origin of the CTA's control window: the first sample of the tile in each dimension
+    int o1 = 0, o2 = 0, o3 = 0;
+    if (TMA) {
+        // TMA needs a 16-byte aligned start address: round the innermost coordinate down
+        o1 = (sg_ldg(a.index[0] + min((int64_t)blockIdx.x * 32 * V1, n1 - 1)) - P - 1) & ~(int)(16 / sizeof(T) - 1);
+        o2 = sg_ldg(a.index[1] + min((int64_t)blockIdx.y * TY * V2, n2 - 1)) - P - 1;
+        o3 = sg_ldg(a.index[2] + j3_lo) - P - 1;
+        if (tid == 0) {
+            sg_mbar_init(mbar, 1);
+            sg_mbar_expect_tx(mbar, (unsigned)TILE_BYTES);
+            sg_tma_load_4d(tile, &tmap, o1, o2, o3, 0, mbar);
+        }
+    }
     __syncthreads();
-    if (j1_0 >= n1 || j2_0 >= n2) return;
+    // NOTE: no thread may exit before the last barrier / mbarrier use when TMA is on
+    const bool in_range = !(j1_0 >= n1 || j2_0 >= n2);
+    if (!TMA && !in_range) return;
 
     T W1[V1][WD], W2[V2][WD];
     int min1, min2;
@@ -133,9 +193,24 @@ __global__ void __launch_bounds__(32 * TY) sg_eval3d_march_kernel(T *__restrict_
     const int nv1 = (int)min((int64_t)V1, n1 - j1_0);
     const int nv2 = (int)min((int64_t)V2, n2 - j2_0);
 
+    // does this thread's padded window fit the staged tile?
+    const bool fits12 = TMA && (min1 - o1 >= 0) && (min1 - o1 + WD <= SG_TMA_B1) && (min2 - o2 >= 0) && (min2 - o2 + WD <= SG_TMA_B2);
+    const T *__restrict__ tbase = tile + (min1 - o1) + SG_TMA_B1 * (min2 - o2);
+
     for (int o = 0; o < o_count; ++o) {
         const T *__restrict__ cpo = cp + a.cp_total * o;
         T *__restrict__ evo = eval + a.n_total * o;
+        if (TMA) {
+            if (o > 0) {   // next output channel: refill the tile (everybody is done reading the previous one)
+                __syncthreads();
+                if (tid == 0) {
+                    sg_mbar_expect_tx(mbar, (unsigned)TILE_BYTES);
+                    sg_tma_load_4d(tile, &tmap, o1, o2, o3, o, mbar);
+                }
+            }
+            sg_mbar_wait(mbar, (unsigned)(o & 1));
+            if (!in_range) continue;
+        }
         if (!(reg1 && reg2)) {   // irregular thread: direct evaluation of every sample it owns
             for (int s = 0; s < nstep; ++s)
                 for (int v2 = 0; v2 < nv2; ++v2)
@@ -157,6 +232,9 @@ __global__ void __launch_bounds__(32 * TY) sg_eval3d_march_kernel(T *__restrict_
 
         auto contract_plane = [&](int64_t i3, T (&out)[V1][V2]) {
             const T *__restrict__ pl = cpo + i3 * c1 * c2;
+            const int p3 = (int)i3 - o3;
+            const bool from_tile = TMA && fits12 && p3 >= 0 && p3 < SG_TMA_B3;
+            const T *__restrict__ tp = tbase + SG_TMA_B1 * SG_TMA_B2 * (from_tile ? p3 : 0);
 #pragma unroll
             for (int v1 = 0; v1 < V1; ++v1)
 #pragma unroll
@@ -164,8 +242,13 @@ __global__ void __launch_bounds__(32 * TY) sg_eval3d_march_kernel(T *__restrict_
 #pragma unroll
             for (int bq = 0; bq < WD; ++bq) {
                 T c[WD];
+                if (from_tile) {
 #pragma unroll
-                for (int aq = 0; aq < WD; ++aq) c[aq] = sg_ldg(pl + row2[bq] + col1[aq]);
+                    for (int aq = 0; aq < WD; ++aq) c[aq] = tp[aq + SG_TMA_B1 * bq];
+                } else {
+#pragma unroll
+                    for (int aq = 0; aq < WD; ++aq) c[aq] = sg_ldg(pl + row2[bq] + col1[aq]);
+                }
 #pragma unroll
                 for (int v1 = 0; v1 < V1; ++v1) {
                     T t1 = T(0);
