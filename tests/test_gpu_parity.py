@@ -297,6 +297,43 @@ def test_slab_sharded_grid_matches_full_grid(S, world):
             S.set_kernel_policy(0)
 
 
+@pytest.mark.parametrize("ft", ["Float32", "Float64"])
+def test_peer_exchange_kernels_single_device(S, ft):
+    """sg_exchange_push / sg_exchange_reduce with all "ranks" simulated on one device (the peer pointers simply
+    point at buffers of the same GPU): the exchanged gradient equals the sum of the partial gradients."""
+    import ctypes as C
+    lib = S._lib.lib()
+    suf = "f32" if ft == "Float32" else "f64"
+    dt = torch.float32 if ft == "Float32" else torch.float64
+    rng = np.random.default_rng(8)
+    world, c1, c2, c_last, nout = 4, 10, 6, 23, 2
+    plane = c1 * c2
+    k0 = [0, 5, 11, 17]
+    npl = [8, 9, 9, 6]                      # supports overlap by 3 planes
+    max_planes = max(npl)
+    grads = []
+    for r in range(world):
+        g = np.zeros((c1, c2, c_last, nout), dtype=np.float64, order="F")
+        g[:, :, k0[r]:k0[r] + npl[r], :] = rng.random((c1, c2, npl[r], nout))
+        grads.append(g)
+    expected = sum(grads)
+    stages = [torch.full((world * nout * max_planes * plane,), float("nan"), dtype=dt, device="cuda") for _ in range(world)]
+    peer = (C.c_void_p * world)(*[t.data_ptr() for t in stages])
+    dev = [S.to_device(g, dtype=dt) for g in grads]
+    for r in range(world):
+        S._lib.check(getattr(lib, "sg_exchange_push_" + suf)(
+            S._lib.ptr(dev[r]), peer, C.c_int(world), C.c_int(r), C.c_int64(plane), C.c_int64(c_last), C.c_int(nout),
+            C.c_int64(k0[r]), C.c_int64(npl[r]), C.c_int64(max_planes), None), "push")
+    torch.cuda.synchronize()
+    for r in range(world):
+        S._lib.check(getattr(lib, "sg_exchange_reduce_" + suf)(
+            S._lib.ptr(dev[r]), S._lib.ptr(stages[r]), C.c_int(world), S._lib.i64_array(k0), S._lib.i64_array(npl),
+            C.c_int64(plane), C.c_int64(c_last), C.c_int(nout), C.c_int64(max_planes), None), "reduce")
+        assert rel_err(S.to_numpy(dev[r]), expected) <= _tol(ft)
+    for r in range(1, world):
+        assert torch.equal(dev[r], dev[0])                          # rank-order summation: bit-identical on every rank
+
+
 def test_nurbs_adjoint_is_transpose_of_forward(S):
     """The NURBS adjoint has no reference behaviour (src/adjoint.jl:52-57): pin it as the exact transpose of our
     own forward map via <R p, e> = <p, R' e>, and as the plain adjoint when all weights are 1."""
@@ -570,6 +607,32 @@ def test_g9_locally_refined_least_squares_fitting(S):
     assert abs(lhs - rhs) <= 1e-12 * abs(lhs)
     fit = _lsqr(A, target)
     assert np.allclose(fit, vals.ravel(order="F"), rtol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# K11 / K12 set-up helpers through the C ABI
+# ---------------------------------------------------------------------------------------------
+
+
+def test_insert_and_collect_indices_kernels(S):
+    """K11 `insert_kernel` (src/util_kernels.jl:69-79) and K12 `collect_indices_kernel` (:81-88)."""
+    import ctypes as C
+    lib = S._lib.lib()
+    rng = np.random.default_rng(0)
+    for npdt, tdt, fn, ctype in ((np.float32, torch.float32, lib.sg_insert_f32, C.c_float),
+                                 (np.float64, torch.float64, lib.sg_insert_f64, C.c_double),
+                                 (np.int32, torch.int32, lib.sg_insert_i32, C.c_int32)):
+        v = (rng.random(37) * 100).astype(npdt)
+        for pos in (1, 19, 38):                                  # 1-based insert position, incl. both ends
+            out = torch.empty(38, dtype=tdt, device="cuda")
+            vin = torch.from_numpy(v).cuda()
+            S._lib.check(fn(S._lib.ptr(out), S._lib.ptr(vin), C.c_int64(37), C.c_int64(pos), ctype(7), None), "sg_insert")
+            assert np.array_equal(out.cpu().numpy(), np.insert(v, pos - 1, npdt(7)))
+    cart = rng.integers(1, 50, size=(123, 3)).astype(np.int64)   # 123 CartesianIndex{3}, AoS
+    idx = torch.empty((3, 123), dtype=torch.int32, device="cuda")   # (123, 3) column-major
+    S._lib.check(lib.sg_collect_indices_i32(S._lib.ptr(idx), S._lib.ptr(torch.from_numpy(cart).cuda()), C.c_int64(123),
+                                            C.c_int(3), None), "sg_collect_indices")
+    assert np.array_equal(idx.cpu().numpy().T, cart.astype(np.int32))
 
 
 # ---------------------------------------------------------------------------------------------
