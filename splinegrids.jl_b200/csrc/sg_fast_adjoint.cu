@@ -281,13 +281,57 @@ static SgFusedPlan sg_adjoint_fused_plan(int nin, const int64_t *n_samples, cons
     return fp;
 }
 
+// ---- 3-D double-march pipeline ---------------------------------------------------------------------------
+struct SgMarch2Plan {
+    bool ok;
+    int G2, tiles2, G3, chunks3;
+    size_t part_off, r_off, bytes;
+};
+#define SG_M2_G2 4
+#define SG_M2_RS 6
+
+static SgMarch2Plan sg_adjoint_march2_plan(int nin, const int64_t *n_samples, const int64_t *n_cp, int nout, const int *degree,
+                                           int elem_size, bool rational)
+{
+    SgMarch2Plan mp{};
+    mp.ok = false;
+    if (rational || nin != 3 || sg_env_int("SG_ADJ_MARCH2", 0) == 0) return mp;
+    const int P = degree[1];
+    if (degree[2] != P || P < 1 || P > 3) return mp;
+    if (n_samples[0] < 128) return mp;
+    mp.G2 = SG_M2_G2;
+    const int64_t nsp2 = n_cp[1] - P, nsp3 = n_cp[2] - P;
+    mp.tiles2 = (int)((nsp2 + mp.G2 - 1) / mp.G2);
+    // enough threads: n1 * tiles2 * chunks3 * nout ~ 128K; chunks are cut over the spans that can hold samples
+    const int64_t base = n_samples[0] * mp.tiles2 * nout;
+    const int64_t chunks_needed = std::max<int64_t>(1, (131072 + base - 1) / base);
+    const int64_t act_spans = std::min<int64_t>(nsp3, n_samples[2]);
+    int64_t G3 = std::max<int64_t>(2, act_spans / chunks_needed);
+    const int forced = sg_env_int("SG_ADJ_M2_G3", 0);
+    if (forced > 0) G3 = forced;
+    G3 = std::min<int64_t>(G3, nsp3);
+    mp.G3 = (int)G3;
+    mp.chunks3 = (int)((nsp3 + G3 - 1) / G3);
+    if ((int64_t)mp.chunks3 * nout > 65535 || mp.tiles2 > 65535 || n_cp[1] > 65535 || n_cp[2] * nout > 65535) return mp;
+    size_t off = 0;
+    mp.part_off = off;
+    off += sg_al256((size_t)n_samples[0] * (mp.G2 + P) * mp.tiles2 * (mp.G3 + P) * mp.chunks3 * nout * elem_size);
+    mp.r_off = off;
+    off += sg_al256((size_t)n_samples[0] * n_cp[1] * n_cp[2] * nout * elem_size);
+    mp.bytes = off;
+    mp.ok = true;
+    return mp;
+}
+
 size_t sg_adjoint_fast_scratch_bytes(int nin, const int64_t *n_samples, const int64_t *n_cp, int nout, const int *degree,
                                      int elem_size)
 {
     if (!sg_adjoint_fast_supported(nin, degree, false)) return 0;
     const size_t a = sg_adjoint_plan(nin, n_samples, n_cp, nout, degree, elem_size).bytes;
     const SgFusedPlan fp = sg_adjoint_fused_plan(nin, n_samples, n_cp, nout, degree, elem_size, false);
-    return std::max(a, fp.ok ? fp.bytes : (size_t)0);   // the two pipelines never run together: they share the scratch
+    const SgMarch2Plan mp = sg_adjoint_march2_plan(nin, n_samples, n_cp, nout, degree, elem_size, false);
+    // the pipelines never run together: they share the scratch
+    return std::max(std::max(a, fp.ok ? fp.bytes : (size_t)0), mp.ok ? mp.bytes : (size_t)0);
 }
 
 template <typename T, int P>
@@ -336,6 +380,64 @@ static int sg_run_fused(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &ss
     return SG_OK;
 }
 
+template <typename T, int P>
+static void sg_launch_march2(const SgAdj2Args<T> &m, int nout, cudaStream_t st)
+{
+    dim3 grid((unsigned)((m.n1 + 127) / 128), (unsigned)m.tiles2, (unsigned)(m.chunks3 * nout));
+    sg_adj_march2_kernel<T, P, SG_M2_G2, SG_M2_RS><<<grid, 128, 0, st>>>(m);
+    g_sg_launches.fetch_add(1);
+}
+
+template <typename T>
+static int sg_run_march2(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &ss, SgAdjointHeader *hdr, const T *eval,
+                         const SgMarch2Plan &mp, char *ws, cudaStream_t st)
+{
+    const int P = a.degree[1];
+    SgAdj2Args<T> m{};
+    T *part = reinterpret_cast<T *>(ws + mp.part_off);
+    T *R = reinterpret_cast<T *>(ws + mp.r_off);
+    m.X = eval; m.Y = part; m.table2 = a.table[1]; m.table3 = a.table[2]; m.index3 = a.index[2];
+    m.start2 = ss.start[1]; m.start3 = ss.start[2]; m.hdr = hdr;
+    m.n1 = a.n_samples[0]; m.n2 = a.n_samples[1]; m.n3 = a.n_samples[2]; m.c2 = a.n_cp[1]; m.c3 = a.n_cp[2];
+    m.tiles2 = mp.tiles2; m.G3 = mp.G3; m.chunks3 = mp.chunks3; m.path = SG_PATH_MULTIPASS;
+    switch (P) {
+        case 1: sg_launch_march2<T, 1>(m, a.nout, st); break;
+        case 2: sg_launch_march2<T, 2>(m, a.nout, st); break;
+        default: sg_launch_march2<T, 3>(m, a.nout, st); break;
+    }
+    dim3 cgrid((unsigned)((m.n1 + 127) / 128), (unsigned)((m.c2 + SG_COMBINE_ROWS - 1) / SG_COMBINE_ROWS), (unsigned)(m.c3 * a.nout));
+    sg_adj_combine2_kernel<T><<<cgrid, 128, 0, st>>>(R, part, hdr, m.n1, m.c2, m.c3, P, mp.G2, mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS);
+    g_sg_launches.fetch_add(1);
+    // pass B over dimension 1 on R (n1, c2, c3, nout); rows of the slowest axis outside the support are skipped
+    const int64_t outerB = a.cp_total / a.n_cp[0] * a.nout;
+    const int64_t avg_range = (int64_t)(a.degree[0] + 1) * a.n_samples[0] / a.n_cp[0];
+    const int b_last_dim = 2, b_last_P = a.degree[2];
+    const int64_t b_last_div = a.n_cp[1], b_last_c = a.n_cp[2];
+    if (avg_range <= 18) {
+        const int rpb = sg_env_int("SG_ADJ_RPB", 8);
+        dim3 rgrid(sg_blocks(a.n_cp[0], 128), (unsigned)((outerB + rpb - 1) / rpb));
+        if (rgrid.y > 65535) return SG_ERR_UNSUPPORTED;
+        sg_adj_first_dim_rows_kernel<T, 20, false><<<rgrid, 128, 0, st>>>(cp, R, a.table[0], a.index[0], ss.start[0], hdr, a.n_samples[0],
+                                                                         a.n_cp[0], outerB, a.degree[0], rpb, nullptr, a.cp_total,
+                                                                         SG_PATH_MULTIPASS, b_last_dim, b_last_P, b_last_div, b_last_c);
+    } else {
+        const unsigned gy = (unsigned)std::min<int64_t>(outerB, 32768);
+        if (avg_range >= 64) {
+            dim3 bgrid(sg_blocks(a.n_cp[0], 256 / 32), gy, (unsigned)((outerB + gy - 1) / gy));
+            sg_adj_first_dim_kernel<T, 32, false><<<bgrid, 256, 0, st>>>(cp, R, a.table[0], a.index[0], ss.start[0], hdr, a.n_samples[0], a.n_cp[0],
+                                                                        outerB, a.degree[0], nullptr, a.cp_total, SG_PATH_MULTIPASS, b_last_dim,
+                                                                        b_last_P, b_last_div, b_last_c);
+        } else {
+            dim3 bgrid(sg_blocks(a.n_cp[0], 256 / 8), gy, (unsigned)((outerB + gy - 1) / gy));
+            sg_adj_first_dim_kernel<T, 8, false><<<bgrid, 256, 0, st>>>(cp, R, a.table[0], a.index[0], ss.start[0], hdr, a.n_samples[0], a.n_cp[0],
+                                                                       outerB, a.degree[0], nullptr, a.cp_total, SG_PATH_MULTIPASS, b_last_dim,
+                                                                       b_last_P, b_last_div, b_last_c);
+        }
+    }
+    g_sg_launches.fetch_add(1);
+    return SG_OK;
+}
+
 template <typename T>
 int sg_evaluate_adjoint_fast(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &ss, SgAdjointHeader *hdr,
                              const T *eval, const T *weights, void *scratch, cudaStream_t st)
@@ -349,10 +451,14 @@ int sg_evaluate_adjoint_fast(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T
 
     SgFusedPlan fp = sg_adjoint_fused_plan(a.nin, a.n_samples, a.n_cp, a.nout, a.degree, (int)sizeof(T), rational);
     if (fp.ok && reinterpret_cast<uintptr_t>(eval) % 16 != 0) fp.ok = false;
+    const SgMarch2Plan mp = sg_adjoint_march2_plan(a.nin, a.n_samples, a.n_cp, a.nout, a.degree, (int)sizeof(T), rational);
     int rc;
     if (fp.ok) {
         rc = sg_run_fused<T>(cp, a, ss, hdr, eval, fp, ws, st);
         g_sg_last_variant = "adjoint_fused_j1";
+    } else if (mp.ok) {
+        rc = sg_run_march2<T>(cp, a, ss, hdr, eval, mp, ws, st);
+        g_sg_last_variant = "adjoint_march2";
     } else {
         rc = sg_run_multipass<T>(cp, a, ss, hdr, eval, weights, ws, SG_PATH_MULTIPASS, st);
         g_sg_last_variant = rational ? "adjoint_passes_rational2d" : "adjoint_passes";

@@ -688,3 +688,205 @@ __global__ void __launch_bounds__(128) sg_adj_tile_combine_kernel(T *__restrict_
         if (i0 < tile_lo[t] + tile_ni[t]) acc += sg_ldg(zr + (i0 - tile_lo[t]) + (int64_t)n_slots * t);
     cp[i0 + c1 * r] = acc;
 }
+
+// =============================================================================================
+// 3-D "double march": contract dimensions 3 AND 2 in one pass, entirely in registers.
+//
+// A thread owns ONE sample column j1 (lanes = consecutive j1: coalesced 8/4-byte loads, full sectors per warp),
+// a tile of G2 whole knot spans of dimension 2 (S = G2+P control slots) and a chunk of G3 spans of dimension 3.
+// For every sample plane j3 it contracts the tile's rows over dimension 2 into T[S] (the slot of a row is
+// (its span - tile start) + k: COMPILE-TIME indices, because the loops run over spans g = 0..G2-1 and, inside
+// a span, over its rows), then marches dimension 3 with the usual P+1 live planes per slot: acc3[S][P+1].
+// When span 3 advances, S completed values leave per thread.  No shared-memory exchange, no atomics; the
+// only block-level sync is the staging of the (CTA-uniform) table rows.
+// Output: partial[j1][slot S][tile2][row3 G3+P][chunk3][o]  (tile/chunk halos are summed by the combine
+// kernel).  For C3 the pass writes ~130 MB instead of the 268 + 67 MB of the two separate passes.
+// Rows of a span are processed RS at a time (any number of samples per span works).
+// =============================================================================================
+template <typename T>
+struct SgAdj2Args {
+    const T *X;                 // eval (n1, n2, n3, nout)
+    T *Y;                       // partials
+    const T *table2, *table3;   // (n2, P+1), (n3, P+1) selected derivative slices
+    const int32_t *index3;
+    const int32_t *start2, *start3;   // span_start arrays
+    const SgAdjointHeader *hdr;
+    int64_t n1, n2, n3, c2, c3;
+    int tiles2, G3, chunks3;
+    int path;
+};
+
+template <typename T, int P, int G2, int RS>
+__global__ void __launch_bounds__(128) sg_adj_march2_kernel(const __grid_constant__ SgAdj2Args<T> a)
+{
+    if (!sg_adj_path_active(a.hdr, a.path)) return;
+    constexpr int S = G2 + P;
+    constexpr int PIECE = 32;
+    __shared__ __align__(16) T b3s[PIECE * (P + 1)];
+    __shared__ int s3s[PIECE];
+    __shared__ int row0[G2 + 1];
+    constexpr int B2ROWS = G2 * RS * 2;                                 // table rows of dimension 2 staged per tile
+    __shared__ __align__(16) T b2s[B2ROWS * (P + 1)];
+
+    const int64_t j1 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int tile2 = blockIdx.y;
+    const int c3k = blockIdx.z % a.chunks3;
+    const int64_t o = blockIdx.z / a.chunks3;
+    const bool active = j1 < a.n1;
+
+    // spans of dimension 2 in this tile: [s2_lo, s2_lo + G2) clipped; rows of span g: [row0[g], row0[g+1])
+    const int s2_lo = P + 1 + tile2 * G2;
+    if (threadIdx.x <= G2) {
+        const int sidx = (int)min((int64_t)s2_lo + threadIdx.x, a.c2 + 1);
+        row0[threadIdx.x] = a.start2[sidx];
+    }
+    __syncthreads();
+    {   // table rows of the tile (rows are contiguous: [row0[0], row0[G2])); rows beyond B2ROWS use global look-ups
+        const int r_first = row0[0], n_rows = min(row0[G2] - row0[0], B2ROWS);
+        for (int q = threadIdx.x; q < n_rows * (P + 1); q += blockDim.x) {
+            const int rr = q / (P + 1), k = q % (P + 1);
+            b2s[q] = sg_ldg(a.table2 + (r_first + rr) + a.n2 * k);
+        }
+    }
+    // spans of dimension 3 in this chunk, restricted to those that hold samples (slabs of a sharded grid)
+    const int s3_lo0 = P + 1 + c3k * a.G3;
+    const int s3_hi0 = (int)min((int64_t)s3_lo0 + a.G3, a.c3 + 1);
+    const int s3_lo = max(s3_lo0, a.hdr->span_first[2]);
+    const int s3_hi = min(s3_hi0, a.hdr->span_last[2] + 1);
+    if (s3_lo >= s3_hi) return;                                        // block-uniform
+    const int64_t j3_lo = a.start3[s3_lo], j3_hi = a.start3[s3_hi];
+    const int rows3 = a.G3 + P;
+
+    T acc3[S][P + 1];
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int k = 0; k <= P; ++k) acc3[s][k] = T(0);
+    int cur = s3_lo;
+
+    const int64_t plane = a.n1 * a.n2;
+    const T *__restrict__ xcol = a.X + j1 + plane * (a.n3 * o);        // + n1*row + plane*j3
+    // Y index = j1 + n1*(slot + S*(tile2 + tiles2*(row3 + rows3*(chunk3 + chunks3*o))))
+    const int64_t y_slot = a.n1;
+    const int64_t y_row3 = a.n1 * (int64_t)S * a.tiles2;
+    T *__restrict__ yp = a.Y + j1 + a.n1 * ((int64_t)S * tile2) + y_row3 * ((int64_t)(s3_lo - s3_lo0) + (int64_t)rows3 * (c3k + (int64_t)a.chunks3 * o));
+
+    auto emit_oldest = [&]() {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            __stcs(yp + y_slot * s, acc3[s][0]);
+#pragma unroll
+            for (int k = 0; k < P; ++k) acc3[s][k] = acc3[s][k + 1];
+            acc3[s][P] = T(0);
+        }
+        yp += y_row3;
+        ++cur;
+    };
+
+    for (int64_t jp = j3_lo; jp < j3_hi; jp += PIECE) {
+        const int np = (int)min((int64_t)PIECE, j3_hi - jp);
+        __syncthreads();
+        for (int s = threadIdx.x; s < np; s += blockDim.x) {
+            s3s[s] = sg_ldg(a.index3 + jp + s);
+#pragma unroll
+            for (int k = 0; k <= P; ++k) b3s[s * (P + 1) + k] = sg_ldg(a.table3 + jp + s + a.n3 * k);
+        }
+        __syncthreads();
+        if (!active) continue;
+        for (int s = 0; s < np; ++s) {
+            const T *__restrict__ xpl = xcol + plane * (jp + s);
+            // ---- contract the tile's rows over dimension 2: T2[g + k] += B2[row, k] * x[row]
+            // all loads of the plane-tile are issued before the first FMA (memory-level parallelism)
+            T x[G2][RS];
+#pragma unroll
+            for (int g = 0; g < G2; ++g)
+#pragma unroll
+                for (int q = 0; q < RS; ++q) x[g][q] = (row0[g] + q < row0[g + 1]) ? __ldcs(xpl + a.n1 * (int64_t)(row0[g] + q)) : T(0);
+            T T2[S];
+#pragma unroll
+            for (int q = 0; q < S; ++q) T2[q] = T(0);
+#pragma unroll
+            for (int g = 0; g < G2; ++g) {
+                const int r_lo = row0[g], r_hi = row0[g + 1];
+#pragma unroll
+                for (int q = 0; q < RS; ++q) {
+                    if (r_lo + q < r_hi) {                              // CTA-uniform
+#pragma unroll
+                        for (int k = 0; k <= P; ++k) {
+                            const int rr = r_lo + q - row0[0];
+                            const T bw = rr < B2ROWS ? b2s[rr * (P + 1) + k] : sg_ldg(a.table2 + (r_lo + q) + a.n2 * k);
+                            T2[g + k] = fma(bw, x[g][q], T2[g + k]);
+                        }
+                    }
+                }
+                for (int rb = r_lo + RS; rb < r_hi; rb += RS) {         // spans with more than RS rows: further batches
+                    T xe[RS];
+#pragma unroll
+                    for (int q = 0; q < RS; ++q) xe[q] = (rb + q < r_hi) ? __ldcs(xpl + a.n1 * (int64_t)(rb + q)) : T(0);
+#pragma unroll
+                    for (int q = 0; q < RS; ++q) {
+                        if (rb + q < r_hi) {
+#pragma unroll
+                            for (int k = 0; k <= P; ++k) T2[g + k] = fma(sg_ldg(a.table2 + (rb + q) + a.n2 * k), xe[q], T2[g + k]);
+                        }
+                    }
+                }
+            }
+            // ---- march dimension 3
+            const int sp = s3s[s];
+            if (cur < sp) {
+                do emit_oldest(); while (cur < sp);
+            }
+            T b[P + 1];
+#pragma unroll
+            for (int k = 0; k <= P; ++k) b[k] = b3s[s * (P + 1) + k];
+#pragma unroll
+            for (int q = 0; q < S; ++q)
+#pragma unroll
+                for (int k = 0; k <= P; ++k) acc3[q][k] = fma(b[k], T2[q], acc3[q][k]);
+        }
+    }
+    if (!active) return;
+    while (cur < s3_hi) emit_oldest();
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) __stcs(yp + y_slot * s + y_row3 * k, acc3[s][k]);
+    }
+}
+
+// R'[j1, i2, i3, o] = sum over tiles of dim 2 covering i2 and chunks of dim 3 covering i3 of the partials.
+// grid = (ceil(n1/128), ceil(c2/SG_COMBINE_ROWS), c3*nout)
+template <typename T>
+__global__ void __launch_bounds__(128) sg_adj_combine2_kernel(T *__restrict__ R, const T *__restrict__ Pp, const SgAdjointHeader *hdr,
+                                                              int64_t n1, int64_t c2, int64_t c3, int P, int G2, int tiles2, int G3,
+                                                              int chunks3, int path)
+{
+    if (!sg_adj_path_active(hdr, path)) return;
+    const int64_t j1 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j1 >= n1) return;
+    const int64_t i3 = (int64_t)(blockIdx.z % c3) + 1;                  // 1-based control indices
+    const int64_t o = blockIdx.z / c3;
+    const int sf = hdr->span_first[2], sl = hdr->span_last[2];
+    if (i3 < sf - P || i3 > sl) return;                                 // outside the support: never read downstream
+    const int S = G2 + P, rows3 = G3 + P;
+    const int64_t c_hi = min((i3 - 1) / G3, (int64_t)chunks3 - 1), c_lo = max((int64_t)0, (i3 - P - 1 + G3) / G3 - 1);
+    const int64_t i2_end = min((int64_t)(blockIdx.y + 1) * SG_COMBINE_ROWS, c2);
+    for (int64_t i2 = (int64_t)blockIdx.y * SG_COMBINE_ROWS + 1; i2 <= i2_end; ++i2) {
+        T acc = T(0);
+        const int64_t t_hi = min((i2 - 1) / G2, (int64_t)tiles2 - 1), t_lo = max((int64_t)0, (i2 - P - 1 + G2) / G2 - 1);
+        for (int64_t c = c_lo; c <= c_hi; ++c) {
+            const int64_t l3 = i3 - (c * G3 + 1);
+            if (l3 < 0 || l3 >= rows3) continue;
+            const int64_t cs_lo = max((int64_t)(P + 1 + c * G3), (int64_t)sf);
+            const int64_t cs_hi = min(min((int64_t)(P + 1 + c * G3 + G3), c3 + 1), (int64_t)sl + 1);
+            if (cs_lo >= cs_hi || i3 < cs_lo - P || i3 > cs_hi - 1) continue;   // rows this chunk really wrote
+            for (int64_t t = t_lo; t <= t_hi; ++t) {
+                const int64_t l2 = i2 - (t * G2 + 1);
+                if (l2 < 0 || l2 >= S) continue;
+                acc += __ldcs(Pp + j1 + n1 * (l2 + (int64_t)S * (t + (int64_t)tiles2 * (l3 + (int64_t)rows3 * (c + (int64_t)chunks3 * o)))));
+            }
+        }
+        R[j1 + n1 * ((i2 - 1) + c2 * ((i3 - 1) + c3 * o))] = acc;
+    }
+}

@@ -201,18 +201,29 @@ def test_evaluate_and_adjoint_vs_oracle(S, case, policy):
 FUSED_CASES = [c for c in CASES if c[2][0] % 64 == 0 and len(c[0]) >= 3]
 
 
-@pytest.mark.parametrize("case", FUSED_CASES, ids=[f"{c[0]}-{c[1]}-{c[4]}" for c in FUSED_CASES])
-def test_fused_adjoint_pipeline_vs_oracle(S, case, monkeypatch):
-    """The opt-in fused adjoint (march along the slowest axis + warp-level contraction of dimension 1,
-    SG_ADJ_FUSED=1) against the C oracle, including tiles with more than 32 control indices."""
+MARCH2_CASES = [((20, 11, 9), (3, 3, 3), (128, 400, 20), 1, "Float64", 0, False),
+                ((100, 8, 6), (2, 2, 2), (128, 400, 20), 1, "Float64", 0, False),
+                ((30, 12, 25), (2, 1, 1), (256, 40, 300), 2, "Float32", 0, False),
+                ((9, 40, 7), (3, 3, 3), (130, 45, 33), 1, "Float64", 0, False)]      # ~1 sample per span in dim 2, ragged n1
+
+
+@pytest.mark.parametrize("case,env,variant",
+                         [(c, "SG_ADJ_FUSED", "adjoint_fused_j1") for c in FUSED_CASES] +
+                         [(c, "SG_ADJ_MARCH2", "adjoint_march2") for c in MARCH2_CASES],
+                         ids=[f"fused-{c[0]}-{c[1]}" for c in FUSED_CASES] + [f"march2-{c[0]}-{c[1]}" for c in MARCH2_CASES])
+def test_optin_adjoint_pipelines_vs_oracle(S, case, env, variant, monkeypatch):
+    """The opt-in experimental adjoint pipelines against the C oracle:
+    SG_ADJ_FUSED=1  -- march along the slowest axis + warp-level contraction of dimension 1 (incl. tiles with
+                       more than 32 control indices);
+    SG_ADJ_MARCH2=1 -- 3-D register-resident double march over dimensions 3 and 2."""
     from gpu_helpers import make_grid, oracle_adjoint
     n_cp, deg, n_s, nout, ft, mdo, nurbs = case
     grid, cp, w, rng = make_grid(n_cp, deg, n_s, nout, ft, mdo=0, seed=21)
     e = np.asfortranarray(rng.random(tuple(n_s) + (nout,)).astype(cp.dtype))
     g = torch.full_like(grid.control_points.obtain(), -3.0)
-    monkeypatch.setenv("SG_ADJ_FUSED", "1")
+    monkeypatch.setenv(env, "1")
     S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g)
-    assert S.last_variant() == "adjoint_fused_j1"
+    assert S.last_variant() == variant
     gref = oracle_adjoint(grid, e)
     assert rel_err(S.to_numpy(g), gref) <= _tol(ft)
     assert max_rel_err(S.to_numpy(g), gref) <= 10 * _tol(ft)
@@ -260,14 +271,16 @@ def test_nonmonotone_sample_points_use_scatter_path(S):
     assert rel_err(S.to_numpy(grid.control_points.obtain()), gref) <= 1e-12
 
 
+@pytest.mark.parametrize("shape", [((9, 8, 40), (3, 2, 3), (40, 36, 96)), ((12, 9, 40), (2, 3, 3), (128, 40, 96))],
+                         ids=["multipass", "march2"])
 @pytest.mark.parametrize("world", [2, 3, 8])
-def test_slab_sharded_grid_matches_full_grid(S, world):
+def test_slab_sharded_grid_matches_full_grid(S, world, shape):
     """Multi-GPU data flow on one device: every rank's slab (sliced last-dimension arrays, replicated control
     points) evaluated separately; concatenated slabs == full evaluate!, summed partial gradients == full adjoint,
     and each partial gradient is non-zero only on the slab's support planes."""
     from gpu_helpers import oracle_adjoint, oracle_evaluate
     rng = np.random.default_rng(4)
-    n_cp, deg, n_s, nout = (9, 8, 40), (3, 2, 3), (40, 36, 96), 2
+    (n_cp, deg, n_s), nout = shape, 2
     gdims = tuple(S.SplineDimension(c, p, n, float_type="Float64") for c, p, n in zip(n_cp, deg, n_s))
     full = S.SplineGrid(gdims, nout)
     cp = np.asfortranarray(rng.random(n_cp + (nout,)))
