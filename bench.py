@@ -290,13 +290,16 @@ def main_gpu(args):
                              "frac_of_hbm_roofline": nb_local / (ms_adj * 1e-3) / 1e9 / hbm,
                              "note": "local kernels only (no all-reduce)"},
     }
-    # dominant kernel = the forward march kernel (one launch == the whole evaluate! call)
-    roofline = {"kernel": "sg_eval3d_march_kernel<double,3,2,4,4> (evaluate!, one launch per call)",
+    # roofline kernel = the forward march kernel (ONE launch == the whole evaluate! call, so its CUDA-event time is
+    # the kernel's launch duration).  The adjoint is a chain of kernels; its op-level fraction is in "also"/"ops".
+    roofline = {"kernel": f"sg_eval3d_march_kernel<double,3,2,4,4,TMA={'true' if var_fwd.endswith('tma') else 'false'}> "
+                          f"[{var_fwd}] (evaluate!, one launch per call)",
+                "share_of_step": ms_fwd / (ms_fwd + ms_adj),
                 "bound": "hbm", "achieved": ops["evaluate"]["achieved_GBs"], "peak": hbm, "unit": "GB/s",
                 "frac": ops["evaluate"]["frac_of_hbm_roofline"], "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                 "algorithmic_bytes_per_launch": nb_local, "traffic": args.traffic_bytes,
-                "traffic_source": "profiles/ (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"
-                if args.traffic_bytes else None,
+                "traffic_source": "profiles/r01_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, "
+                                  "N=1 full grid)" if args.traffic_bytes else None,
                 "also": {"evaluate_adjoint_op_frac": ops["evaluate_adjoint"]["frac_of_hbm_roofline"]}}
 
     # ---- end-to-end through the public API with HOST buffers -------------------------------------
@@ -374,6 +377,10 @@ def main():
                     help="DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.traffic_bytes is None:     # DRAM traffic of the roofline kernel from the committed ncu capture
+        tp = ROOT / "profiles" / "r01_traffic.json"
+        if tp.exists():
+            args.traffic_bytes = float(json.loads(tp.read_text())["total"])
     if args.impl == "reference":
         return main_reference(args)
     return main_gpu(args)
