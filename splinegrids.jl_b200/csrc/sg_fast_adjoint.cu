@@ -295,7 +295,11 @@ static SgMarch2Plan sg_adjoint_march2_plan(int nin, const int64_t *n_samples, co
 {
     SgMarch2Plan mp{};
     mp.ok = false;
-    if (rational || nin != 3 || sg_env_int("SG_ADJ_MARCH2", 0) == 0) return mp;
+    // SG_ADJ_MARCH2: 0 = never, 1 = always when eligible, unset = when the slowest axis is densely sampled (a thin slab
+    // of a sharded grid touches few control planes: the chunked multi-pass pipeline is better there)
+    const int mode = sg_env_int("SG_ADJ_MARCH2", -1);
+    if (rational || nin != 3 || mode == 0) return mp;
+    if (mode < 0 && n_samples[2] < 2 * (n_cp[2] - degree[2])) return mp;
     const int P = degree[1];
     if (degree[2] != P || P < 1 || P > 3) return mp;
     if (n_samples[0] < 128) return mp;
@@ -304,7 +308,7 @@ static SgMarch2Plan sg_adjoint_march2_plan(int nin, const int64_t *n_samples, co
     mp.tiles2 = (int)((nsp2 + mp.G2 - 1) / mp.G2);
     // enough threads: n1 * tiles2 * chunks3 * nout ~ 128K; chunks are cut over the spans that can hold samples
     const int64_t base = n_samples[0] * mp.tiles2 * nout;
-    const int64_t chunks_needed = std::max<int64_t>(1, (131072 + base - 1) / base);
+    const int64_t chunks_needed = std::max<int64_t>(1, (294912 + base - 1) / base);   // ~300K threads (G3 ~ 7 on C3) measured best
     const int64_t act_spans = std::min<int64_t>(nsp3, n_samples[2]);
     int64_t G3 = std::max<int64_t>(2, act_spans / chunks_needed);
     const int forced = sg_env_int("SG_ADJ_M2_G3", 0);
@@ -380,12 +384,28 @@ static int sg_run_fused(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &ss
     return SG_OK;
 }
 
+#define SG_M2_RTMAX 20
+#define SG_M2_NS 3
 template <typename T, int P>
-static void sg_launch_march2(const SgAdj2Args<T> &m, int nout, cudaStream_t st)
+static int sg_launch_march2(const SgAdj2Args<T> &m, int nout, cudaStream_t st)
 {
     dim3 grid((unsigned)((m.n1 + 127) / 128), (unsigned)m.tiles2, (unsigned)(m.chunks3 * nout));
-    sg_adj_march2_kernel<T, P, SG_M2_G2, SG_M2_RS><<<grid, 128, 0, st>>>(m);
+    // TMA-fed ring: bulk copies need 16-byte aligned rows; rows per tile are data dependent, so the expected count must
+    // fit the ring (tiles that do not are skipped by the TMA kernel and done by the register kernel right after)
+    const bool tma_ok = sg_env_int("SG_ADJ_M2_TMA", 1) && (m.n1 * sizeof(T)) % 16 == 0 && reinterpret_cast<uintptr_t>(m.X) % 16 == 0 &&
+                        (double)m.n2 / (double)std::max<int64_t>(1, m.c2 - P) * SG_M2_G2 <= SG_M2_RTMAX - 2;
+    if (tma_ok) {
+        auto kern = sg_adj_march2_tma_kernel<T, P, SG_M2_G2, SG_M2_RTMAX, SG_M2_NS>;
+        const size_t smem = sizeof(T) * SG_M2_NS * SG_M2_RTMAX * 128;
+        SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 160, smem, st>>>(m);                                   // 4 consumer warps + 1 producer warp
+        sg_adj_march2_kernel<T, P, SG_M2_G2, SG_M2_RS><<<grid, 128, 0, st>>>(m, SG_M2_RTMAX);   // tiles with more rows (normally none)
+        g_sg_launches.fetch_add(2);
+        return SG_OK;
+    }
+    sg_adj_march2_kernel<T, P, SG_M2_G2, SG_M2_RS><<<grid, 128, 0, st>>>(m, 0);
     g_sg_launches.fetch_add(1);
+    return SG_OK;
 }
 
 template <typename T>
@@ -400,13 +420,24 @@ static int sg_run_march2(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &s
     m.start2 = ss.start[1]; m.start3 = ss.start[2]; m.hdr = hdr;
     m.n1 = a.n_samples[0]; m.n2 = a.n_samples[1]; m.n3 = a.n_samples[2]; m.c2 = a.n_cp[1]; m.c3 = a.n_cp[2];
     m.tiles2 = mp.tiles2; m.G3 = mp.G3; m.chunks3 = mp.chunks3; m.path = SG_PATH_MULTIPASS;
+    int lrc;
     switch (P) {
-        case 1: sg_launch_march2<T, 1>(m, a.nout, st); break;
-        case 2: sg_launch_march2<T, 2>(m, a.nout, st); break;
-        default: sg_launch_march2<T, 3>(m, a.nout, st); break;
+        case 1: lrc = sg_launch_march2<T, 1>(m, a.nout, st); break;
+        case 2: lrc = sg_launch_march2<T, 2>(m, a.nout, st); break;
+        default: lrc = sg_launch_march2<T, 3>(m, a.nout, st); break;
     }
-    dim3 cgrid((unsigned)((m.n1 + 127) / 128), (unsigned)((m.c2 + SG_COMBINE_ROWS - 1) / SG_COMBINE_ROWS), (unsigned)(m.c3 * a.nout));
-    sg_adj_combine2_kernel<T><<<cgrid, 128, 0, st>>>(R, part, hdr, m.n1, m.c2, m.c3, P, mp.G2, mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS);
+    if (lrc != SG_OK) return lrc;
+    if (sg_env_int("SG_ADJ_M2_SCAN", 1) && mp.G3 >= P && a.nout <= 65535) {
+        dim3 sgrid((unsigned)((m.n1 + 127) / 128), (unsigned)m.c3, (unsigned)a.nout);
+        switch (P) {
+            case 1: sg_adj_combine2_scan_kernel<T, 1, SG_M2_G2><<<sgrid, 128, 0, st>>>(R, part, hdr, m.n1, m.c2, m.c3, mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS); break;
+            case 2: sg_adj_combine2_scan_kernel<T, 2, SG_M2_G2><<<sgrid, 128, 0, st>>>(R, part, hdr, m.n1, m.c2, m.c3, mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS); break;
+            default: sg_adj_combine2_scan_kernel<T, 3, SG_M2_G2><<<sgrid, 128, 0, st>>>(R, part, hdr, m.n1, m.c2, m.c3, mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS); break;
+        }
+    } else {
+        dim3 cgrid((unsigned)((m.n1 + 127) / 128), (unsigned)((m.c2 + SG_COMBINE_ROWS - 1) / SG_COMBINE_ROWS), (unsigned)(m.c3 * a.nout));
+        sg_adj_combine2_kernel<T><<<cgrid, 128, 0, st>>>(R, part, hdr, m.n1, m.c2, m.c3, P, mp.G2, mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS);
+    }
     g_sg_launches.fetch_add(1);
     // pass B over dimension 1 on R (n1, c2, c3, nout); rows of the slowest axis outside the support are skipped
     const int64_t outerB = a.cp_total / a.n_cp[0] * a.nout;

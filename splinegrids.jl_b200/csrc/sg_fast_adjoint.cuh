@@ -717,7 +717,7 @@ struct SgAdj2Args {
 };
 
 template <typename T, int P, int G2, int RS>
-__global__ void __launch_bounds__(128) sg_adj_march2_kernel(const __grid_constant__ SgAdj2Args<T> a)
+__global__ void __launch_bounds__(128) sg_adj_march2_kernel(const __grid_constant__ SgAdj2Args<T> a, int only_tiles_above_rows)
 {
     if (!sg_adj_path_active(a.hdr, a.path)) return;
     constexpr int S = G2 + P;
@@ -741,6 +741,8 @@ __global__ void __launch_bounds__(128) sg_adj_march2_kernel(const __grid_constan
         row0[threadIdx.x] = a.start2[sidx];
     }
     __syncthreads();
+    // complement of the TMA-fed kernel: only the tiles it skipped (more rows than its ring holds)
+    if (only_tiles_above_rows > 0 && row0[G2] - row0[0] <= only_tiles_above_rows) return;   // block-uniform
     {   // table rows of the tile (rows are contiguous: [row0[0], row0[G2])); rows beyond B2ROWS use global look-ups
         const int r_first = row0[0], n_rows = min(row0[G2] - row0[0], B2ROWS);
         for (int q = threadIdx.x; q < n_rows * (P + 1); q += blockDim.x) {
@@ -889,4 +891,226 @@ __global__ void __launch_bounds__(128) sg_adj_combine2_kernel(T *__restrict__ R,
         }
         R[j1 + n1 * ((i2 - 1) + c2 * ((i3 - 1) + c3 * o))] = acc;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA-fed variant of the double march: the tile's rows of each sample plane (n_rows x 128 columns) are streamed
+// into an NS-stage shared-memory ring with 1-D bulk async copies (cp.async.bulk, one per row, issued by one
+// elected thread, completion counted on an mbarrier per stage), NS-1 planes ahead of the consumers.  Loads no
+// longer occupy registers or stall the math: the kernel becomes bandwidth-bound.  Tiles with more than RTMAX rows
+// (or a ragged / misaligned n1) are handled by sg_adj_march2_kernel instead (host + device checks).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sg_bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sg_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(sg_smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void sg_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sg_smem_u32(bar)) : "memory");
+}
+
+// Warp-specialised: warps 0-3 (128 threads) consume, warp 4 produces (one elected lane issues the bulk copies).
+// full[st]  : producer -> consumers, completes when the plane's bytes have landed (expect_tx)
+// empty[st] : consumers -> producer, 128 arrivals once every consumer has read the stage
+// No block-wide barrier inside the plane loop; the (CTA-uniform) dimension-3 table rows are staged per piece of
+// MAXPL planes.
+template <typename T, int P, int G2, int RTMAX, int NS>
+__global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_constant__ SgAdj2Args<T> a)
+{
+    if (!sg_adj_path_active(a.hdr, a.path)) return;
+    constexpr int S = G2 + P;
+    constexpr int MAXPL = 128;                                          // planes per staged piece of dim-3 tables
+    constexpr int CW = 128;                                             // columns per CTA == consumer threads
+    extern __shared__ __align__(128) unsigned char sg_smem2[];
+    T *xs = reinterpret_cast<T *>(sg_smem2);                            // [NS][RTMAX][CW]
+    __shared__ __align__(16) T b3s[MAXPL * (P + 1)];
+    __shared__ int s3s[MAXPL];
+    __shared__ int row0[G2 + 1];
+    __shared__ __align__(16) T b2s[RTMAX * (P + 1)];
+    __shared__ __align__(8) uint64_t full[NS];
+    __shared__ __align__(8) uint64_t empty[NS];
+
+    const int tid = threadIdx.x;
+    const bool is_producer = tid >= CW;
+    const int64_t j1_0 = (int64_t)blockIdx.x * CW;
+    const int64_t j1 = j1_0 + tid;
+    const int tile2 = blockIdx.y;
+    const int c3k = blockIdx.z % a.chunks3;
+    const int64_t o = blockIdx.z / a.chunks3;
+    const bool active = !is_producer && j1 < a.n1;
+    const int ncols = (int)min((int64_t)CW, a.n1 - j1_0);
+
+    const int s2_lo = P + 1 + tile2 * G2;
+    if (tid <= G2) row0[tid] = a.start2[(int)min((int64_t)s2_lo + tid, a.c2 + 1)];
+    if (tid == 0) {
+#pragma unroll
+        for (int q = 0; q < NS; ++q) { sg_mbar_init(&full[q], 1); sg_mbar_init(&empty[q], CW); }
+    }
+    __syncthreads();
+    const int r_first = row0[0], n_rows = row0[G2] - row0[0];
+    if (n_rows > RTMAX) return;                                         // block-uniform: the register kernel takes this tile
+    for (int q = tid; q < n_rows * (P + 1); q += blockDim.x) b2s[q] = sg_ldg(a.table2 + (r_first + q / (P + 1)) + a.n2 * (q % (P + 1)));
+
+    const int s3_lo0 = P + 1 + c3k * a.G3;
+    const int s3_hi0 = (int)min((int64_t)s3_lo0 + a.G3, a.c3 + 1);
+    const int s3_lo = max(s3_lo0, a.hdr->span_first[2]);
+    const int s3_hi = min(s3_hi0, a.hdr->span_last[2] + 1);
+    if (s3_lo >= s3_hi) return;                                        // block-uniform
+    const int64_t j3_lo = a.start3[s3_lo], j3_hi = a.start3[s3_hi];
+    const int np_total = (int)(j3_hi - j3_lo);
+    const int rows3 = a.G3 + P;
+
+    T acc3[S][P + 1];
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int k = 0; k <= P; ++k) acc3[s][k] = T(0);
+    int cur = s3_lo;
+
+    const int64_t plane = a.n1 * a.n2;
+    const T *__restrict__ xtile = a.X + j1_0 + a.n1 * (int64_t)r_first + plane * (a.n3 * o + j3_lo);
+    const int64_t y_slot = a.n1;
+    const int64_t y_row3 = a.n1 * (int64_t)S * a.tiles2;
+    T *__restrict__ yp = a.Y + j1 + a.n1 * ((int64_t)S * tile2) + y_row3 * ((int64_t)(s3_lo - s3_lo0) + (int64_t)rows3 * (c3k + (int64_t)a.chunks3 * o));
+    const unsigned row_bytes = (unsigned)(ncols * sizeof(T));
+
+    auto emit_oldest = [&]() {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            __stcs(yp + y_slot * s, acc3[s][0]);
+#pragma unroll
+            for (int k = 0; k < P; ++k) acc3[s][k] = acc3[s][k + 1];
+            acc3[s][P] = T(0);
+        }
+        yp += y_row3;
+        ++cur;
+    };
+
+    for (int p0 = 0; p0 < np_total; p0 += MAXPL) {
+        const int p1 = min(p0 + MAXPL, np_total);
+        __syncthreads();                                                // consumers are done with the previous piece's tables
+        for (int s = tid; s < p1 - p0; s += blockDim.x) {
+            s3s[s] = sg_ldg(a.index3 + j3_lo + p0 + s);
+#pragma unroll
+            for (int k = 0; k <= P; ++k) b3s[s * (P + 1) + k] = sg_ldg(a.table3 + j3_lo + p0 + s + a.n3 * k);
+        }
+        __syncthreads();
+        if (is_producer) {
+            if (tid == CW && n_rows > 0) {                              // one elected lane feeds the ring
+                for (int p = p0; p < p1; ++p) {
+                    const int st = p % NS, k = p / NS;
+                    if (k > 0) sg_mbar_wait(&empty[st], (unsigned)((k - 1) & 1));   // every consumer has read the previous plane in this stage
+                    sg_mbar_expect_tx(&full[st], row_bytes * (unsigned)n_rows);
+                    const T *src = xtile + plane * (int64_t)p;
+                    T *dst = xs + (size_t)st * RTMAX * CW;
+                    for (int r = 0; r < n_rows; ++r) sg_bulk_g2s(dst + r * CW, src + a.n1 * (int64_t)r, row_bytes, &full[st]);
+                }
+            }
+            continue;
+        }
+        for (int p = p0; p < p1; ++p) {
+            const int st = p % NS;
+            T T2[S];
+#pragma unroll
+            for (int q = 0; q < S; ++q) T2[q] = T(0);
+            if (n_rows > 0) {
+                sg_mbar_wait(&full[st], (unsigned)((p / NS) & 1));
+                const T *__restrict__ xst = xs + (size_t)st * RTMAX * CW + tid;
+                // ---- contract the tile's rows over dimension 2 (values come from the shared-memory ring)
+#pragma unroll
+                for (int g = 0; g < G2; ++g) {
+                    const int r_lo = row0[g] - r_first, r_hi = row0[g + 1] - r_first;
+                    for (int r = r_lo; r < r_hi; ++r) {
+                        const T x = xst[r * CW];
+#pragma unroll
+                        for (int k = 0; k <= P; ++k) T2[g + k] = fma(b2s[r * (P + 1) + k], x, T2[g + k]);
+                    }
+                }
+                sg_mbar_arrive(&empty[st]);                             // this thread no longer needs the stage
+            }
+            if (!active) continue;
+            // ---- march dimension 3
+            const int sl = p - p0;
+            const int sp = s3s[sl];
+            if (cur < sp) {
+                do emit_oldest(); while (cur < sp);
+            }
+            T b[P + 1];
+#pragma unroll
+            for (int k = 0; k <= P; ++k) b[k] = b3s[sl * (P + 1) + k];
+#pragma unroll
+            for (int q = 0; q < S; ++q)
+#pragma unroll
+                for (int k = 0; k <= P; ++k) acc3[q][k] = fma(b[k], T2[q], acc3[q][k]);
+        }
+    }
+    if (!active) return;
+    while (cur < s3_hi) emit_oldest();
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) __stcs(yp + y_slot * s + y_row3 * k, acc3[s][k]);
+    }
+}
+
+// Combine of the double-march partials as a sequential scan over the tiles of dimension 2 (needs G2 >= P, so only
+// neighbouring tiles overlap): a thread owns (j1, i3, o), walks the tiles t = 0..tiles2-1 and carries the P halo
+// slots from one tile to the next.  No integer divisions, all loads/stores coalesced along j1.
+// grid = (ceil(n1/128), c3, nout)
+template <typename T, int P, int G2>
+__global__ void __launch_bounds__(128) sg_adj_combine2_scan_kernel(T *__restrict__ R, const T *__restrict__ Pp, const SgAdjointHeader *hdr,
+                                                                   int64_t n1, int64_t c2, int64_t c3, int tiles2, int G3, int chunks3, int path)
+{
+    if (!sg_adj_path_active(hdr, path)) return;
+    constexpr int S = G2 + P;
+    const int64_t j1 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j1 >= n1) return;
+    const int64_t i3 = (int64_t)blockIdx.y + 1;                         // 1-based control index of dimension 3
+    const int64_t o = blockIdx.z;
+    const int sf = hdr->span_first[2], sl = hdr->span_last[2];
+    if (i3 < sf - P || i3 > sl) return;                                 // outside the support: never read downstream
+    const int rows3 = G3 + P;
+    // the (<= 2 when G3 >= P) chunks of dimension 3 whose written rows contain i3
+    int64_t cc[4], ll[4];
+    int nc = 0;
+    const int64_t c_hi = min((i3 - 1) / G3, (int64_t)chunks3 - 1), c_lo = max((int64_t)0, (i3 - P - 1 + G3) / G3 - 1);
+    for (int64_t c = c_lo; c <= c_hi && nc < 4; ++c) {
+        const int64_t l3 = i3 - (c * G3 + 1);
+        if (l3 < 0 || l3 >= rows3) continue;
+        const int64_t cs_lo = max((int64_t)(P + 1 + c * G3), (int64_t)sf);
+        const int64_t cs_hi = min(min((int64_t)(P + 1 + c * G3 + G3), c3 + 1), (int64_t)sl + 1);
+        if (cs_lo >= cs_hi || i3 < cs_lo - P || i3 > cs_hi - 1) continue;
+        cc[nc] = c; ll[nc] = l3; ++nc;
+    }
+    T carry[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) carry[k] = T(0);
+    T *__restrict__ out = R + j1 + n1 * (c2 * ((i3 - 1) + c3 * o));
+    const int64_t t_stride = n1 * (int64_t)S;                           // between tiles
+    for (int t = 0; t < tiles2; ++t) {
+        T v[S];
+#pragma unroll
+        for (int q = 0; q < S; ++q) v[q] = T(0);
+        for (int e = 0; e < nc; ++e) {
+            const T *__restrict__ src = Pp + j1 + t_stride * (t + (int64_t)tiles2 * (ll[e] + (int64_t)rows3 * (cc[e] + (int64_t)chunks3 * o)));
+#pragma unroll
+            for (int q = 0; q < S; ++q) v[q] += __ldcs(src + n1 * q);
+        }
+#pragma unroll
+        for (int k = 0; k < P; ++k) v[k] += carry[k];
+        const int64_t i2_0 = (int64_t)t * G2;                           // 0-based control index of slot 0
+#pragma unroll
+        for (int q = 0; q < G2; ++q)
+            if (i2_0 + q < c2) out[n1 * (i2_0 + q)] = v[q];
+#pragma unroll
+        for (int k = 0; k < P; ++k) carry[k] = v[G2 + k];
+    }
+    // the last tile's halo slots are real control indices (c2 = nspans + P)
+    const int64_t i2_0 = (int64_t)tiles2 * G2;
+#pragma unroll
+    for (int k = 0; k < P; ++k)
+        if (i2_0 + k < c2) out[n1 * (i2_0 + k)] = carry[k];
 }
