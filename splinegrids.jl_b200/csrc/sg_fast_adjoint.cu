@@ -7,6 +7,7 @@
 #include "sg_evaluate_generic.cuh"
 #include "sg_fast.cuh"
 #include "sg_fast_adjoint.cuh"
+#include "sg_adjoint_march3.cuh"
 #include "sg_fast_eval.cuh"
 
 static int sg_env_int(const char *name, int dflt)
@@ -327,6 +328,161 @@ static SgMarch2Plan sg_adjoint_march2_plan(int nin, const int64_t *n_samples, co
     return mp;
 }
 
+
+// ---- 3-D single-pass pipeline (sg_adjoint_march3.cuh) ---------------------------------------------------
+#define SG_M3_DEFAULT_MODE 0   // opt-in until it beats the double march on C3
+struct SgMarch3Plan {
+    bool ok;
+    int P, W, nb1, tiles2, L1, L3, maxseg;
+    size_t smem;
+    size_t mask_off, mask_bytes, part_off, bytes;
+};
+
+static size_t sg_m3_smem_bytes(int elem_size, int P)
+{
+    const size_t S2 = SG_M3_G2 + P;
+    return (size_t)elem_size * ((size_t)SG_M3_NS * SG_M3_G2 * SG_M3_RPT * SG_M3_CW + S2 * SG_M3_PITCH + (size_t)SG_M3_G2 * 4 * SG_M3_CW +
+                                (size_t)4 * SG_M3_PITCH + (size_t)SG_M3_G2 * SG_M3_RPT * 4 + (size_t)SG_M3_MAXPL * 4) +
+           sizeof(int) * SG_M3_MAXPL + 128;
+}
+
+template <typename T>
+static const void *sg_m3_kernel_ptr(int P)
+{
+    switch (P) {
+        case 1: return reinterpret_cast<const void *>(&sg_adj_march3_kernel<T, 1>);
+        case 2: return reinterpret_cast<const void *>(&sg_adj_march3_kernel<T, 2>);
+        default: return reinterpret_cast<const void *>(&sg_adj_march3_kernel<T, 3>);
+    }
+}
+
+// resident workers for the persistent grid: SMs x CTAs per SM at this shared-memory size
+static int sg_m3_workers(int elem_size, int P, size_t smem)
+{
+    const int forced = sg_env_int("SG_ADJ_M3_W", 0);
+    if (forced > 0) return forced;
+    int dev = 0, sms = 148, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const void *k = elem_size == 4 ? sg_m3_kernel_ptr<float>(P) : sg_m3_kernel_ptr<double>(P);
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, SG_M3_NCONS + 32, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return sms * per_sm;
+}
+
+static SgMarch3Plan sg_adjoint_march3_plan(int nin, const int64_t *n_samples, const int64_t *n_cp, int nout, const int *degree,
+                                           int elem_size, bool rational)
+{
+    SgMarch3Plan mp{};
+    mp.ok = false;
+    // SG_ADJ_MARCH3: 0 = never, 1 = whenever the hard constraints hold, 2 = densely sampled grids only (auto rule)
+    const int mode = sg_env_int("SG_ADJ_MARCH3", SG_M3_DEFAULT_MODE);
+    if (rational || nin != 3 || mode == 0) return mp;
+    const int P = degree[1];
+    if (degree[2] != P || P < 1 || P > 3 || degree[0] < 1 || degree[0] > 5) return mp;
+    if ((n_samples[0] * elem_size) % 16 != 0) return mp;                 // bulk copies: 16-byte rows
+    const int64_t nsp1 = n_cp[0] - degree[0], nsp2 = n_cp[1] - P, nsp3 = n_cp[2] - P;
+    const bool forced = mode == 1 || g_sg_policy == 2;
+    if (!forced) {
+        if (n_samples[0] < 2 * SG_M3_CW) return mp;
+        if (n_samples[1] < nsp2 || n_samples[2] < nsp3) return mp;       // sparse sampling: the partial buffer would dominate
+        if (degree[0] > 3 || n_samples[0] < nsp1) return mp;               // dimension 1: fast contraction only
+        if (n_samples[1] > 2 * SG_M3_RPT * nsp2) return mp;               // many rows per span: several passes, other pipelines win
+    }
+    mp.P = P;
+    mp.nb1 = (int)((n_samples[0] + SG_M3_CW - 1) / SG_M3_CW);
+    mp.tiles2 = (int)((nsp2 + SG_M3_G2 - 1) / SG_M3_G2);
+    const int64_t ncols = (int64_t)nout * mp.nb1 * mp.tiles2;
+    if (n_cp[1] > 65535 || n_cp[2] * nout > 65535 || ncols > (1 << 24)) return mp;
+    mp.smem = sg_m3_smem_bytes(elem_size, P);
+    mp.W = sg_m3_workers(elem_size, P, mp.smem);
+    if (mp.W <= 0) return mp;
+    // small problems: at least ~4 planes per worker and at most ~8 segments per (block, tile) column
+    const int64_t col_equiv = std::max<int64_t>(1, (int64_t)nout * mp.nb1 * nsp2 / SG_M3_G2);
+    mp.W = (int)std::min<int64_t>(mp.W, std::max<int64_t>(1, std::min<int64_t>(col_equiv * 8, col_equiv * n_samples[2] / 4)));
+    // segments per (block, tile) column: a tile of G2 spans holds ~G2/nsp2 of the rows of its column block, which is
+    // shared by W / (nout*nb1) workers; x2 for uneven knot spans.  Columns that need more fall back on device.
+    mp.maxseg = (int)((2 * (int64_t)mp.W * SG_M3_G2 + (int64_t)nout * mp.nb1 * nsp2 - 1) / ((int64_t)nout * mp.nb1 * nsp2)) + 3;
+    mp.maxseg = std::min(mp.maxseg, 32);                                  // bits of the row mask
+    mp.L1 = (int)(n_cp[0] + (int64_t)mp.nb1 * (degree[0] + 1));
+    mp.L3 = (int)(n_cp[2] + (int64_t)mp.maxseg * (P + 1));
+    size_t off = 0;
+    mp.mask_off = off;
+    mp.mask_bytes = (size_t)ncols * n_cp[2] * sizeof(unsigned);
+    off += sg_al256(mp.mask_bytes);
+    mp.part_off = off;
+    off += sg_al256((size_t)mp.L1 * (SG_M3_G2 + P) * mp.tiles2 * mp.L3 * nout * elem_size);
+    mp.bytes = off;
+    mp.ok = true;
+    return mp;
+}
+
+typedef CUresult (*SgEncodeTiledFn3)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static SgEncodeTiledFn3 sg_m3_encoder()
+{
+    static SgEncodeTiledFn3 fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<SgEncodeTiledFn3>(p);
+    }();
+    return fn;
+}
+
+// eval as a 3-D tensor (n1, n2, n3*nout), boxes (CW, 16 >> i, 1)
+template <typename T>
+static bool sg_m3_make_maps(SgM3Maps &maps, const T *eval, int64_t n1, int64_t n2, int64_t n3nout)
+{
+    SgEncodeTiledFn3 enc = sg_m3_encoder();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)n1, (cuuint64_t)n2, (cuuint64_t)n3nout};
+    cuuint64_t strides[2] = {(cuuint64_t)n1 * sizeof(T), (cuuint64_t)n1 * n2 * sizeof(T)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    for (int i = 0; i < SG_M3_NMAPS; ++i) {
+        cuuint32_t box[3] = {SG_M3_CW, (cuuint32_t)(16 >> i), 1};
+        if (enc(&maps.m[i], dt, 3, const_cast<T *>(eval), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    return true;
+}
+
+template <typename T>
+static int sg_run_march3(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &ss, SgAdjointHeader *hdr, const T *eval,
+                         const SgMarch3Plan &mp, char *ws, cudaStream_t st)
+{
+    SgAdj3Args<T> m{};
+    m.X = eval;
+    m.part = reinterpret_cast<T *>(ws + mp.part_off);
+    m.rowmask = reinterpret_cast<unsigned *>(ws + mp.mask_off);
+    m.table1 = a.table[0]; m.table2 = a.table[1]; m.table3 = a.table[2];
+    m.index1 = a.index[0]; m.index3 = a.index[2];
+    m.start1 = ss.start[0]; m.start2 = ss.start[1];
+    m.hdr = hdr;
+    m.n1 = a.n_samples[0]; m.n2 = a.n_samples[1]; m.n3 = a.n_samples[2];
+    m.c1 = a.n_cp[0]; m.c2 = a.n_cp[1]; m.c3 = a.n_cp[2];
+    m.P1 = a.degree[0];
+    m.nb1 = mp.nb1; m.tiles2 = mp.tiles2; m.nout = a.nout;
+    m.L1 = mp.L1; m.L3 = mp.L3; m.maxseg = mp.maxseg;
+    SgM3Maps maps;
+    if (!sg_m3_make_maps<T>(maps, eval, m.n1, m.n2, m.n3 * a.nout)) return SG_ERR_UNSUPPORTED;
+    SG_CUDA(cudaMemsetAsync(m.rowmask, 0, mp.mask_bytes, st));
+    switch (mp.P) {
+        case 1: sg_adj_march3_kernel<T, 1><<<mp.W, SG_M3_NCONS + 32, mp.smem, st>>>(m, maps); break;
+        case 2: sg_adj_march3_kernel<T, 2><<<mp.W, SG_M3_NCONS + 32, mp.smem, st>>>(m, maps); break;
+        default: sg_adj_march3_kernel<T, 3><<<mp.W, SG_M3_NCONS + 32, mp.smem, st>>>(m, maps); break;
+    }
+    dim3 cgrid(sg_blocks(m.c1, 128), (unsigned)m.c2, (unsigned)(m.c3 * a.nout));
+    sg_adj_combine3_kernel<T><<<cgrid, 128, 0, st>>>(cp, m.part, m.rowmask, hdr, m.index1, m.n1, m.c1, m.c2, m.c3, m.P1, mp.P, SG_M3_G2,
+                                                     mp.nb1, mp.tiles2, mp.L1, mp.L3);
+    g_sg_launches.fetch_add(2);
+    return SG_OK;
+}
+
 size_t sg_adjoint_fast_scratch_bytes(int nin, const int64_t *n_samples, const int64_t *n_cp, int nout, const int *degree,
                                      int elem_size)
 {
@@ -334,8 +490,9 @@ size_t sg_adjoint_fast_scratch_bytes(int nin, const int64_t *n_samples, const in
     const size_t a = sg_adjoint_plan(nin, n_samples, n_cp, nout, degree, elem_size).bytes;
     const SgFusedPlan fp = sg_adjoint_fused_plan(nin, n_samples, n_cp, nout, degree, elem_size, false);
     const SgMarch2Plan mp = sg_adjoint_march2_plan(nin, n_samples, n_cp, nout, degree, elem_size, false);
+    const SgMarch3Plan m3 = sg_adjoint_march3_plan(nin, n_samples, n_cp, nout, degree, elem_size, false);
     // the pipelines never run together: they share the scratch
-    return std::max(std::max(a, fp.ok ? fp.bytes : (size_t)0), mp.ok ? mp.bytes : (size_t)0);
+    return std::max(std::max(std::max(a, fp.ok ? fp.bytes : (size_t)0), mp.ok ? mp.bytes : (size_t)0), m3.ok ? m3.bytes : (size_t)0);
 }
 
 template <typename T, int P>
@@ -477,14 +634,20 @@ int sg_evaluate_adjoint_fast(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T
     if (!sg_adjoint_fast_supported(a.nin, a.degree, rational)) return SG_ERR_UNSUPPORTED;
     if (g_sg_policy != 2 && a.n_total < 32768) return SG_ERR_UNSUPPORTED;
     char *ws = static_cast<char *>(scratch);
-    // zero fill (src/adjoint.jl:61): needed only if the prep kernel flags non-monotone spans (scatter path)
-    SG_CUDA(cudaMemsetAsync(cp, 0, (size_t)a.cp_total * a.nout * sizeof(T), st));
+    SgMarch3Plan m3 = sg_adjoint_march3_plan(a.nin, a.n_samples, a.n_cp, a.nout, a.degree, (int)sizeof(T), rational);
+    if (m3.ok && reinterpret_cast<uintptr_t>(eval) % 16 != 0) m3.ok = false;
+    // zero fill (src/adjoint.jl:61): needed only if the prep kernel flags non-monotone spans (scatter path); the
+    // single-pass pipeline's combine kernel does it itself
+    if (!m3.ok) SG_CUDA(cudaMemsetAsync(cp, 0, (size_t)a.cp_total * a.nout * sizeof(T), st));
 
     SgFusedPlan fp = sg_adjoint_fused_plan(a.nin, a.n_samples, a.n_cp, a.nout, a.degree, (int)sizeof(T), rational);
     if (fp.ok && reinterpret_cast<uintptr_t>(eval) % 16 != 0) fp.ok = false;
     const SgMarch2Plan mp = sg_adjoint_march2_plan(a.nin, a.n_samples, a.n_cp, a.nout, a.degree, (int)sizeof(T), rational);
     int rc;
-    if (fp.ok) {
+    if (m3.ok) {
+        rc = sg_run_march3<T>(cp, a, ss, hdr, eval, m3, ws, st);
+        g_sg_last_variant = "adjoint_march3";
+    } else if (fp.ok) {
         rc = sg_run_fused<T>(cp, a, ss, hdr, eval, fp, ws, st);
         g_sg_last_variant = "adjoint_fused_j1";
     } else if (mp.ok) {

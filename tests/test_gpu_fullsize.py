@@ -68,19 +68,22 @@ def test_c3_full_size_3d_cubic_float64(S):
     y.copy_(torch.rand(y.shape, dtype=y.dtype, device="cuda", generator=g))
     grad = torch.zeros_like(cp)
     S.evaluate_adjoint_(grid, eval=y, control_points=grad)
-    assert S.last_variant() in ("adjoint_march2", "adjoint_passes")
+    assert S.last_variant() in ("adjoint_march3", "adjoint_march2")
     lhs, rhs = _dot(ev, y), _dot(cp, grad)
     assert abs(lhs - rhs) <= 1e-11 * abs(lhs)
-    # ... and the multi-pass pipeline gives the same gradient as the (default) double-march pipeline
+    # ... and the single-pass, double-march and multi-pass pipelines give the same gradient
     import os
-    grad2 = torch.zeros_like(cp)
-    os.environ["SG_ADJ_MARCH2"] = "0"
-    try:
-        S.evaluate_adjoint_(grid, eval=y, control_points=grad2)
-        assert S.last_variant() == "adjoint_passes"
-    finally:
-        del os.environ["SG_ADJ_MARCH2"]
-    assert rel_err(S.to_numpy(grad2), S.to_numpy(grad)) <= 1e-12
+    for env, variant in (({"SG_ADJ_MARCH3": "1"}, "adjoint_march3"), ({"SG_ADJ_MARCH3": "0"}, "adjoint_march2"),
+                         ({"SG_ADJ_MARCH3": "0", "SG_ADJ_MARCH2": "0"}, "adjoint_passes")):
+        grad2 = torch.zeros_like(cp)
+        os.environ.update(env)
+        try:
+            S.evaluate_adjoint_(grid, eval=y, control_points=grad2)
+            assert S.last_variant() == variant
+        finally:
+            for k in env:
+                del os.environ[k]
+        assert rel_err(S.to_numpy(grad2), S.to_numpy(grad)) <= 1e-12
     # adjoint of a one-hot plane pattern equals basis sums: e == 1 => grad[i] = prod_d sum_j B_d[j, i]
     y.fill_(1.0)
     S.evaluate_adjoint_(grid, eval=y, control_points=grad)
