@@ -27,16 +27,15 @@
 #pragma once
 #include "sg_fast_adjoint.cuh"
 
-#define SG_M3_CW 64           // columns (samples of dimension 1) per worker
+#define SG_M3_CW 128          // columns (samples of dimension 1) per worker
 #define SG_M3_G2 4            // knot spans of dimension 2 per tile; consumer threads = CW * G2
 #define SG_M3_RPT 5           // rows of a span handled per pass (stage rows = G2 * RPT)
-#define SG_M3_NS 8            // ring stages
-#define SG_M3_MINB 2          // CTAs per SM
-#define SG_M3_NSPMAX 36       // knot spans of dimension 1 per column block handled by the fast contraction
+#define SG_M3_NS 5            // ring stages
+#define SG_M3_NSPMAX 40       // knot spans of dimension 1 per column block handled by the fast contraction
 #define SG_M3_PITCH (SG_M3_CW + SG_M3_CW / 4 + 4)   // skewed row of the park buffer: index j + (j >> 2)
 #define SG_M3_MAXPL 64        // planes per staged piece of the dimension-3 tables
-#define SG_M3_MOUT 2          // outputs per thread with precomputed descriptors
 #define SG_M3_NCONS (SG_M3_CW * SG_M3_G2)
+#define SG_M3_THREADS (SG_M3_NCONS + 32)   // consumers + producer warp
 
 template <typename T>
 struct SgAdj3Args {
@@ -118,59 +117,57 @@ __device__ __forceinline__ void sg_lds4(uint32_t a, float (&w)[4])
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w[0]), "=f"(w[1]), "=f"(w[2]), "=f"(w[3]) : "r"(a));
 }
 
-// Linear partition: iterates over the segments of worker w.  Every thread that needs the sequence (producer lanes and
-// consumers) runs its own copy: closed-form integer arithmetic on start2 only.
-template <int P, int G2>
+// Linear partition: iterates over the segments of worker w.  Every thread that needs the sequence (the producer warp and
+// consumer thread 0) runs its own copy.  The unit of work is one pass over one plane of one (block, tile) column -- the
+// cost of a plane hardly depends on the number of rows of the tile, only on the number of passes it needs -- so a column
+// weighs cumw[t+1] - cumw[t] = passes(t) (0 for tiles without samples) per plane; cumw lives in shared memory.
+#define SG_M3_MAXTILES 1024
 struct SgM3SegIter {
-    int64_t o_begin, o_end, tot, tot1, n2, n3, c2;
-    const int32_t *start2;
+    int64_t o_begin, o_end, tot, tot1, n3, nob;
+    const int *cumw;
     int W, w, tiles2;
     int64_t ob;      // index over (o, b1)
     int t;           // tile of the NEXT candidate column
     // current segment
     int64_t col_ob;
-    int col_t, r_first, n_rows, p0, p1, kseg;
+    int col_t, p0, p1, kseg;
 
-    __device__ __forceinline__ int cum(int tt) const { return start2[(int)min((int64_t)P + 1 + (int64_t)G2 * tt, c2 + 1)]; }
-
-    __device__ void init(int w_, int W_, int64_t nob, int64_t n2_, int64_t n3_, int64_t c2_, int tiles2_, const int32_t *start2_)
+    __device__ void init(int w_, int W_, int64_t nob_, int64_t n3_, int tiles2_, const int *cumw_)
     {
-        W = W_; w = w_; n2 = n2_; n3 = n3_; c2 = c2_; tiles2 = tiles2_; start2 = start2_;
-        tot1 = n2 * n3;
+        W = W_; w = w_; n3 = n3_; tiles2 = tiles2_; cumw = cumw_; nob = nob_;
+        tot1 = (int64_t)cumw[tiles2] * n3;
         tot = nob * tot1;
         o_begin = (int64_t)w * tot / W;
         o_end = (int64_t)(w + 1) * tot / W;
-        ob = o_begin / tot1;
-        const int64_t rq = (o_begin % tot1) / n3;      // largest t with cum(t) <= rq
+        ob = tot1 > 0 ? o_begin / tot1 : nob;
+        const int64_t rq = tot1 > 0 ? (o_begin % tot1) / n3 : 0;   // largest t with cumw[t] <= rq
         int lo = 0, hi = tiles2 - 1;
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
-            if (cum(mid) <= rq) lo = mid; else hi = mid - 1;
+            if (cumw[mid] <= rq) lo = mid; else hi = mid - 1;
         }
         t = lo;
         if (o_begin >= o_end) ob = nob;                  // empty worker
-        nob_ = nob;
     }
-    int64_t nob_;
 
     __device__ bool next()
     {
-        while (ob < nob_) {
-            const int c0 = cum(t), c1 = cum(t + 1);
-            const int64_t A = (ob * n2 + c0) * n3;
+        while (ob < nob) {
+            const int c0 = cumw[t], c1 = cumw[t + 1];
+            const int64_t A = (ob * cumw[tiles2] + c0) * n3;
             if (A >= o_end) return false;
-            const int rows = c1 - c0;
+            const int wt = c1 - c0;
             const int64_t my_ob = ob;
             const int my_t = t;
             if (++t == tiles2) { t = 0; ++ob; }
-            if (rows <= 0) continue;
-            // plane p of the column belongs to the worker that holds its first unit A + p*rows
+            if (wt <= 0) continue;
+            // plane p of the column belongs to the worker that holds its first unit A + p*wt
             const int64_t d0 = o_begin - A, d1 = o_end - A;
-            const int64_t q0 = d0 <= 0 ? 0 : (d0 + rows - 1) / rows;
-            const int64_t q1 = (d1 + rows - 1) / rows;
+            const int64_t q0 = d0 <= 0 ? 0 : (d0 + wt - 1) / wt;
+            const int64_t q1 = (d1 + wt - 1) / wt;
             const int pp0 = (int)min(q0, n3), pp1 = (int)min(q1, n3);
             if (pp0 >= pp1) continue;
-            col_ob = my_ob; col_t = my_t; r_first = c0; n_rows = rows; p0 = pp0; p1 = pp1;
+            col_ob = my_ob; col_t = my_t; p0 = pp0; p1 = pp1;
             const int64_t w_first = ((A + 1) * W + tot - 1) / tot - 1;   // worker that holds unit A
             kseg = (int)(w - w_first);
             return true;
@@ -179,60 +176,93 @@ struct SgM3SegIter {
     }
 };
 
+// Descriptor of a control plane travelling through the post pipeline
+struct SgM3RowMeta {
+    long long base_off;   // element offset of the partial row (without the block's first control index)
+    int b1;               // column block
+    int flags;            // bit 0: store, bit 1: first pass (store; else add), bit 2: valid row, bit 3: block-constants buffer
+};
+// Column-block constants used by the dimension-1 contraction (two blocks can be in flight)
+struct SgM3Block {
+    int lo_b, nsp_b, ni1, fast, ncols;
+    long long j1_0;
+};
+
 template <typename T, int P>
-__global__ void __launch_bounds__(SG_M3_NCONS + 32, SG_M3_MINB) sg_adj_march3_kernel(const __grid_constant__ SgAdj3Args<T> a, const __grid_constant__ SgM3Maps maps)
+__global__ void __launch_bounds__(SG_M3_THREADS, 1) sg_adj_march3_kernel(const __grid_constant__ SgAdj3Args<T> a, const __grid_constant__ SgM3Maps maps)
 {
     if (a.hdr->nonmonotone) return;
     constexpr int G2 = SG_M3_G2;
     constexpr int S2 = G2 + P;
     constexpr int CW = SG_M3_CW;
     constexpr int NCONS = SG_M3_NCONS;
+    constexpr int NW = NCONS / 32;                                      // consumer warps
     constexpr int RPT = SG_M3_RPT;
     constexpr int NROWS = G2 * RPT;                                     // row slots of a ring stage
     constexpr int NS = SG_M3_NS;
+    constexpr int NQ = 3;                                               // row buffers of the post pipeline
     constexpr int PITCH = SG_M3_PITCH;
     constexpr int MAXPL = SG_M3_MAXPL;
-    constexpr int MOUT = SG_M3_MOUT;
     constexpr int NSPMAX = SG_M3_NSPMAX;
-    static_assert(NROWS <= 32, "one producer lane per stage row");
-    static_assert(S2 * 4 * NSPMAX <= G2 * 4 * CW, "the span sums of dimension 1 alias the span partials of dimension 2");
-    static_assert(NSPMAX * S2 <= NCONS, "one (span, slot) unit per consumer thread");
+    static_assert(NROWS <= 31, "a run of stage rows is decomposed in boxes of 16, 8, 4, 2, 1 rows");
     static_assert((CW & (CW - 1)) == 0, "CW must be a power of two");
+    static_assert(NSPMAX * S2 <= NCONS && (NSPMAX + 3) * S2 <= NCONS, "one dimension-1 unit / output per consumer thread");
+    static_assert(S2 <= 2 * G2, "two control slots per consumer thread");
     extern __shared__ __align__(16) unsigned char sg_smem3[];          // NOT declared 128-aligned: the compiler would fold the fix-up below
     // TMA destinations must be 128-byte aligned in the shared window (the dynamic region starts after the static
     // variables at an offset that is only 16-byte aligned): the host adds 128 bytes of slack
     T *ring = reinterpret_cast<T *>(sg_smem3 + ((128u - (sg_smem_u32(sg_smem3) & 127u)) & 127u));   // [NS][NROWS][CW]
-    T *park = ring + (size_t)NS * NROWS * CW;                           // [S2][PITCH]   control slots x columns (skewed)
-    T *t4 = park + S2 * PITCH;                                          // [G2][4][CW]   span partials of dim 2; aliased by
-                                                                        // [S2][4][NSPMAX] span sums of dim 1
-    T *wAB = t4 + G2 * 4 * CW;                                          // [2][PITCH][2] B1[j, 0:2], B1[j, 2:4] of the block's columns
-    T *b2s = wAB + 4 * PITCH;                                           // [NROWS][4]    B2 rows of the stage rows (0 if absent)
+    T *tq = ring + (size_t)NS * NROWS * CW;                             // [NQ][G2][4][CW]    span partials of dimension 2
+    T *park = tq + (size_t)NQ * G2 * 4 * CW;                            // [NQ][S2][PITCH]    control slots x columns (skewed)
+    T *a4 = park + (size_t)NQ * S2 * PITCH;                             // [NQ][S2][4][NSPMAX] span sums of dimension 1
+    T *wAB = a4 + (size_t)NQ * S2 * 4 * NSPMAX;                         // [2][2][PITCH][2]   B1[j, 0:2], B1[j, 2:4] per block parity
+    T *b2s = wAB + 2 * 4 * PITCH;                                       // [NROWS][4]         B2 rows of the stage rows (0 if absent)
     T *b3s = b2s + NROWS * 4;                                           // [MAXPL][4]
     int *s3s = reinterpret_cast<int *>(b3s + MAXPL * 4);                // [MAXPL]
     __shared__ __align__(8) uint64_t full[NS];
     __shared__ __align__(8) uint64_t empty[NS];
+    __shared__ __align__(8) uint64_t pbar[3][NQ];                       // phase k of the row in buffer q is complete (all warps)
+    __shared__ SgM3RowMeta qmeta[8];                                    // by (row step & 7): a warp may lag almost two steps behind the writer
+    __shared__ SgM3Block blk[2];
+    __shared__ int cumw[SG_M3_MAXTILES + 1];                            // prefix sums of the passes per plane of every tile
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const bool is_producer = tid >= NCONS;
     if (tid == 0) {
 #pragma unroll
-        for (int q = 0; q < NS; ++q) { sg_mbar_init(&full[q], 1); sg_mbar_init(&empty[q], NCONS / 32); }
+        for (int q = 0; q < NS; ++q) { sg_mbar_init(&full[q], 1); sg_mbar_init(&empty[q], NW); }
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) sg_mbar_init(&pbar[k][q], NW);
+    }
+    for (int t = threadIdx.x; t < a.tiles2; t += blockDim.x) {          // passes of tile t: ceil(longest span / RPT)
+        int maxnr = 0;
+#pragma unroll
+        for (int gg = 0; gg < G2; ++gg) {
+            const int r_a = a.start2[(int)min((int64_t)P + 1 + (int64_t)G2 * t + gg, a.c2 + 1)];
+            const int r_b = a.start2[(int)min((int64_t)P + 1 + (int64_t)G2 * t + gg + 1, a.c2 + 1)];
+            maxnr = max(maxnr, r_b - r_a);
+        }
+        cumw[t + 1] = (maxnr + RPT - 1) / RPT;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        cumw[0] = 0;
+        for (int t = 0; t < a.tiles2; ++t) cumw[t + 1] += cumw[t];
     }
     __syncthreads();
 
-    const int64_t plane = a.n1 * a.n2;
-    int st = 0;
-    unsigned ph = 0;
-
-    if (is_producer) {
-        // ---------------- producer warp: lane l = stage row (g, q) issues the bulk copy of its row ----------------
-        SgM3SegIter<P, G2> it;
-        it.init((int)blockIdx.x, (int)gridDim.x, (int64_t)a.nout * a.nb1, a.n2, a.n3, a.c2, a.tiles2, a.start2);
-        // The whole producer warp runs this loop converged; single-thread operations elect a lane inside the asm.
+    if (tid >= NCONS) {
+        // ======================= producer warp =======================
+        // The whole warp runs this loop converged; single-thread operations elect a lane inside the asm.
         // Single-pass tiles (no span with more than RPT rows): the tile's rows are contiguous in the plane and land at
         // stage row (row - first row of the tile).  Otherwise every span's rows of the pass land at stage row g*RPT.
         // Each run of rows is fetched as the binary decomposition of its length in TMA boxes (1-2 copies per stage).
+        SgM3SegIter it;
+        it.init((int)blockIdx.x, (int)gridDim.x, (int64_t)a.nout * a.nb1, a.n3, a.tiles2, cumw);
+        int st = 0;
+        unsigned ph = 0;
         bool first_round = true;
         const uint32_t ring_s = sg_smem_u32(ring), full_s = sg_smem_u32(full), empty_s = sg_smem_u32(empty);
         while (it.next()) {
@@ -283,44 +313,155 @@ __global__ void __launch_bounds__(SG_M3_NCONS + 32, SG_M3_MINB) sg_adj_march3_ke
         return;
     }
 
-    // ---------------- consumers: thread = (column, span g of the tile) ----------------
+    // ======================= consumers: thread = (column, span g of the tile) =======================
     // the segment sequence is advanced by thread 0 on an iterator that lives in shared memory
-    __shared__ SgM3SegIter<P, G2> it;
+    __shared__ SgM3SegIter it;
     __shared__ int it_has;
-    if (tid == 0) it.init((int)blockIdx.x, (int)gridDim.x, (int64_t)a.nout * a.nb1, a.n2, a.n3, a.c2, a.tiles2, a.start2);
+    if (tid == 0) it.init((int)blockIdx.x, (int)gridDim.x, (int64_t)a.nout * a.nb1, a.n3, a.tiles2, cumw);
     const int col = tid & (CW - 1), g = tid / CW;
     const int colskew = col + (col >> 2);
-    int cur_b1 = -1;
-    int ni1 = 0, lo_b = 0;                      // control indices of the block: lo_b .. lo_b + ni1 - 1 (1-based)
-    int nsp_b = 0;                              // knot spans of dimension 1 touched by the block
-    bool fast_block = false;
-    int64_t j1_0 = 0;
-    int ncols = 0;
+    int st = 0;
+    unsigned ph = 0;
+    int cur_b1 = -1, blk_par = 1;               // blk_par toggles with every new column block (two can be in flight)
     const uint32_t ring_c = sg_smem_u32(ring) + (uint32_t)(col * sizeof(T));
     const uint32_t b2_u = sg_smem_u32(b2s) + (uint32_t)(g * RPT * 4 * sizeof(T)), b3_u = sg_opaque(sg_smem_u32(b3s));
-    const uint32_t park_u = sg_smem_u32(park), wab_u = sg_smem_u32(wAB);
     const uint32_t full_u = sg_opaque(sg_smem_u32(full)), empty_u = sg_opaque(sg_smem_u32(empty));
+    const uint32_t pbar_u = sg_smem_u32(pbar);
     const uint32_t s3_u = sg_opaque(sg_smem_u32(s3s));
-    // dimension-1 span unit of this thread (fast blocks): span usl of the block, slot uslot, its columns [uc0, uc1)
-    int usl = 0, uslot = 0, uc0 = 0, uc1 = 0;
-    // descriptors of this thread's outputs om = tid + NCONS*m: il | slot << 16 | valid << 31
-    unsigned od[MOUT];
-#pragma unroll
-    for (int m = 0; m < MOUT; ++m) od[m] = 0;
+    const uint32_t park_u = sg_smem_u32(park), wab_u = sg_smem_u32(wAB);
 
-    // slow contraction of one output over dimension 1 (any range length / number of control indices / degree)
-    auto gather_slow = [&](int il, int slot) -> T {
-        const int64_t i = (int64_t)lo_b + il;
-        const int64_t s0 = i > a.P1 + 1 ? i : a.P1 + 1;
-        const int64_t s1 = i + a.P1 < a.c1 ? i + a.P1 : a.c1;
-        const int64_t lo = max((int64_t)a.start1[s0], j1_0), hi = min((int64_t)a.start1[s1 + 1], j1_0 + ncols);
-        T sum = T(0);
-        for (int64_t j = lo; j < hi; ++j) {
-            const int k = (int)(i - sg_ldg(a.index1 + j) + a.P1);
-            const int jj = (int)(j - j1_0);
-            sum = fma(sg_ldg(a.table1 + j + a.n1 * k), park[slot * PITCH + jj + (jj >> 2)], sum);
+    // ---- post pipeline: at step e (one per queued control plane) a warp runs
+    //   phase 1 of row e   (span partial over dimension 2 -> tq),           arrives pbar[0]
+    //   phase 2 of row e-1 (control slots: park = sum of span partials),     arrives pbar[1]
+    //   phase 3 of row e-2 (span sums over dimension 1: a4),                 arrives pbar[2]
+    //   phase 4 of row e-3 (control indices -> partials in global memory).
+    // Every wait is on a barrier the other warps arrived at one step (>= one knot span of planes) earlier, so in steady
+    // state nobody blocks; rows use buffer (step % 3), which is provably free again three steps later (warps are at most
+    // one step apart because of the waits).
+    unsigned step = 0;                          // pipeline steps taken so far by this thread
+    auto wait_phase = [&](int k, unsigned row_step) {   // phase k+1 of the row queued at step row_step is complete
+        sg_mbar_wait_u(pbar_u + (uint32_t)((k * NQ + (int)(row_step % NQ)) * 8), (row_step / NQ) & 1u);
+    };
+    auto arrive_phase = [&](int k, unsigned row_step) {
+        __syncwarp();
+        if (lane == 0) sg_mbar_arrive_u(pbar_u + (uint32_t)((k * NQ + (int)(row_step % NQ)) * 8));
+    };
+    // t: this thread's span partial of the new row (phase 1 input); meta written by thread 0
+    auto pipeline_step = [&](bool new_row, const T (&t)[4], int64_t base_off, int b1, int flags) {
+        const unsigned e = step;
+        {   // ---- phase 1 (row e)
+            const int qb = (int)(e % NQ);
+            if (new_row) {
+                T *__restrict__ dst = tq + ((size_t)qb * G2 * 4 + g * 4) * CW + col;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) dst[k * CW] = t[k];
+            }
+            if (tid == 0) {
+                qmeta[e & 7].base_off = base_off;
+                qmeta[e & 7].b1 = b1;
+                qmeta[e & 7].flags = new_row ? (flags | 4) : 0;
+            }
+            arrive_phase(0, e);
         }
-        return sum;
+        if (e >= 1) {   // ---- phase 2 (row e-1): park[slot][col] = sum_{g'+k = slot} tq[g'][k][col], slots g and g+G2
+            const unsigned r = e - 1;
+            const int qb = (int)(r % NQ);
+            wait_phase(0, r);
+            if (qmeta[r & 7].flags & 4) {
+                const T *__restrict__ tqs = tq + (size_t)qb * G2 * 4 * CW + col;
+                T *__restrict__ pk = park + (size_t)qb * S2 * PITCH + colskew;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int slot = g + h * G2;
+                    if (slot < S2) {
+                        T v = T(0);
+#pragma unroll
+                        for (int gg = 0; gg < G2; ++gg) {
+                            const int k = slot - gg;
+                            if (k >= 0 && k <= P) v += tqs[(gg * 4 + k) * CW];
+                        }
+                        pk[slot * PITCH] = v;
+                    }
+                }
+            }
+            arrive_phase(1, r);
+        }
+        if (e >= 2) {   // ---- phase 3 (row e-2): A[sl][slot][e'] = sum_{j in span sl} B1[j,e'] * park[slot][j]
+            const unsigned r = e - 2;
+            const int qb = (int)(r % NQ);
+            wait_phase(1, r);
+            const SgM3RowMeta m = qmeta[r & 7];
+            if (m.flags & 4) {
+                const SgM3Block &B = blk[(m.flags >> 3) & 1];
+                if (B.fast && tid < B.nsp_b * S2) {
+                    const int sl = tid % B.nsp_b, slot = tid / B.nsp_b;
+                    const int64_t j1_0 = B.j1_0;
+                    const int c0 = (int)(max((int64_t)a.start1[B.lo_b + a.P1 + sl], j1_0) - j1_0);
+                    const int c1 = (int)(min((int64_t)a.start1[B.lo_b + a.P1 + sl + 1], j1_0 + B.ncols) - j1_0);
+                    T A[4] = {T(0), T(0), T(0), T(0)};
+                    const uint32_t xb = park_u + (uint32_t)(((size_t)qb * S2 + slot) * PITCH * sizeof(T));
+                    const uint32_t wb = wab_u + (uint32_t)(((m.flags >> 3) & 1) * 4 * PITCH * sizeof(T));
+                    for (int j = c0; j < c1; ++j) {
+                        const uint32_t jsk = (uint32_t)(j + (j >> 2));
+                        T w[4];
+                        sg_lds2(wb + jsk * (uint32_t)(2 * sizeof(T)), w[0], w[1]);
+                        sg_lds2(wb + (PITCH + jsk) * (uint32_t)(2 * sizeof(T)), w[2], w[3]);
+                        const T x = sg_lds(xb + jsk * (uint32_t)sizeof(T), T(0));
+#pragma unroll
+                        for (int ee = 0; ee < 4; ++ee) A[ee] = fma(w[ee], x, A[ee]);
+                    }
+                    T *__restrict__ ad = a4 + ((size_t)qb * S2 + slot) * 4 * NSPMAX + sl;
+#pragma unroll
+                    for (int ee = 0; ee < 4; ++ee) ad[ee * NSPMAX] = A[ee];
+                } else if (!B.fast) {
+                    // sparse sampling / high degree in dimension 1: direct table look-ups on the parked control slots,
+                    // written straight to the partials (park is only guaranteed intact during this phase)
+                    T *__restrict__ prow = a.part + m.base_off + ((int64_t)(B.lo_b - 1) + (int64_t)m.b1 * (a.P1 + 1));
+                    const bool store_ok = m.flags & 1, first_pass = m.flags & 2;
+                    const T *__restrict__ pk = park + (size_t)qb * S2 * PITCH;
+                    for (int om = tid; om < B.ni1 * S2; om += NCONS) {
+                        const int il = om % B.ni1, slot = om / B.ni1;
+                        const int64_t i = (int64_t)B.lo_b + il;
+                        const int64_t s0 = i > a.P1 + 1 ? i : a.P1 + 1;
+                        const int64_t s1 = i + a.P1 < a.c1 ? i + a.P1 : a.c1;
+                        const int64_t lo = max((int64_t)a.start1[s0], (int64_t)B.j1_0), hi = min((int64_t)a.start1[s1 + 1], (int64_t)B.j1_0 + B.ncols);
+                        T sum = T(0);
+                        for (int64_t j = lo; j < hi; ++j) {
+                            const int k = (int)(i - sg_ldg(a.index1 + j) + a.P1);
+                            const int jj = (int)(j - B.j1_0);
+                            sum = fma(sg_ldg(a.table1 + j + a.n1 * k), pk[slot * PITCH + jj + (jj >> 2)], sum);
+                        }
+                        if (store_ok) { T *dst = prow + il + (int64_t)a.L1 * slot; *dst = first_pass ? sum : *dst + sum; }
+                    }
+                }
+            }
+            arrive_phase(2, r);
+        }
+        if (e >= 3) {   // ---- phase 4 (row e-3): out[il][slot] = sum_e' A[il - e'][slot][e'] -> partials
+            const unsigned r = e - 3;
+            const int qb = (int)(r % NQ);
+            wait_phase(2, r);
+            const SgM3RowMeta m = qmeta[r & 7];
+            if (m.flags & 4) {
+                const SgM3Block &B = blk[(m.flags >> 3) & 1];
+                T *__restrict__ prow = a.part + m.base_off + ((int64_t)(B.lo_b - 1) + (int64_t)m.b1 * (a.P1 + 1));
+                const bool store_ok = m.flags & 1, first_pass = m.flags & 2;
+                if (B.fast) {
+                    if (tid < B.ni1 * S2) {
+                        const int il = tid % B.ni1, slot = tid / B.ni1;
+                        const T *__restrict__ as = a4 + ((size_t)qb * S2 + slot) * 4 * NSPMAX;
+                        T sum = T(0);
+#pragma unroll
+                        for (int ee = 0; ee < 4; ++ee) {
+                            const int sl = il - ee;
+                            if (ee <= a.P1 && sl >= 0 && sl < B.nsp_b) sum += as[ee * NSPMAX + sl];
+                        }
+                        if (store_ok) { T *dst = prow + il + (int64_t)a.L1 * slot; *dst = first_pass ? sum : *dst + sum; }
+                    }
+                }
+            }
+        }
+        ++step;
     };
 
     while (true) {
@@ -338,31 +479,23 @@ __global__ void __launch_bounds__(SG_M3_NCONS + 32, SG_M3_MINB) sg_adj_march3_ke
         if (!store_ok && tid == 0) a.hdr->nonmonotone = 1;   // never with sane sample distributions: the scatter kernel
                                                              // takes over (the ring is still drained in step)
         if (b1 != cur_b1) {
-            // ---- basis weights of dimension 1 for the block's columns, span units, output descriptors
+            // ---- new column block: its constants and B1 rows go to the other buffer; rows of the previous block that are
+            // still in the post pipeline keep using theirs (a segment queues >= P+1 rows, the pipeline holds 3)
             cur_b1 = b1;
-            j1_0 = (int64_t)b1 * CW;
-            ncols = (int)min((int64_t)CW, a.n1 - j1_0);
+            blk_par ^= 1;
+            const int64_t j1_0 = (int64_t)b1 * CW;
+            const int ncols = (int)min((int64_t)CW, a.n1 - j1_0);
             const int first = sg_ldg(a.index1 + j1_0), last = sg_ldg(a.index1 + j1_0 + ncols - 1);
-            lo_b = first - a.P1;
-            nsp_b = last - first + 1;
-            ni1 = nsp_b + a.P1;
-            fast_block = nsp_b <= NSPMAX && a.P1 <= 3;
+            if (tid == 0) {
+                SgM3Block &B = blk[blk_par];
+                B.lo_b = first - a.P1; B.nsp_b = last - first + 1; B.ni1 = last - first + 1 + a.P1;
+                B.fast = (last - first + 1 <= NSPMAX && a.P1 <= 3) ? 1 : 0; B.ncols = ncols; B.j1_0 = j1_0;
+            }
             if (tid < ncols) {
+                T *__restrict__ wd = wAB + (size_t)blk_par * 4 * PITCH;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    wAB[((k >> 1) * PITCH + colskew) * 2 + (k & 1)] = k <= a.P1 ? sg_ldg(a.table1 + j1_0 + tid + a.n1 * k) : T(0);
-            }
-            usl = tid % nsp_b;
-            uslot = tid / nsp_b;
-            uc0 = uc1 = 0;
-            if (fast_block && uslot < S2) {
-                uc0 = (int)(max((int64_t)a.start1[first + usl], j1_0) - j1_0);
-                uc1 = (int)(min((int64_t)a.start1[first + usl + 1], j1_0 + ncols) - j1_0);
-            }
-#pragma unroll
-            for (int m = 0; m < MOUT; ++m) {
-                const int om = tid + NCONS * m;
-                od[m] = om < ni1 * S2 ? ((unsigned)(om % ni1) | ((unsigned)(om / ni1) << 16) | (1u << 31)) : 0u;
+                    wd[((k >> 1) * PITCH + colskew) * 2 + (k & 1)] = k <= a.P1 ? sg_ldg(a.table1 + j1_0 + tid + a.n1 * k) : T(0);
             }
         }
         // rows of this thread's span g of the tile, and the longest span (block-uniform)
@@ -378,11 +511,10 @@ __global__ void __launch_bounds__(SG_M3_NCONS + 32, SG_M3_MINB) sg_adj_march3_ke
         const int s3_first = sg_ldg(a.index3 + seg_p0), s3_last = sg_ldg(a.index3 + seg_p1 - 1);
         // partial index = pos1 + L1*(slot + S2*(tile2 + tiles2*(rowpos + L3*o)))
         const int64_t row_stride = (int64_t)a.L1 * S2 * a.tiles2;
-        T *__restrict__ pcol = a.part + ((int64_t)(lo_b - 1) + (int64_t)b1 * (a.P1 + 1)) + (int64_t)a.L1 * S2 * tile2 + row_stride * ((int64_t)a.L3 * o);
+        const int64_t col_off = (int64_t)a.L1 * S2 * tile2 + row_stride * ((int64_t)a.L3 * o + (int64_t)kseg * (P + 1));
 
         for (int r_off = 0; r_off < maxnr; r_off += RPT) {                // passes (one unless a span has > RPT rows)
-            const bool first_pass = r_off == 0;
-            sg_m3_consumer_bar();               // the previous pass no longer reads b2s
+            sg_m3_consumer_bar();               // the previous pass no longer reads b2s; block constants are visible
             if (tid < NROWS * 4) {              // B2 rows of the stage rows of this pass, zero for absent rows
                 const int l = tid >> 2, k = tid & 3;
                 const int gg = l / RPT, qq = l % RPT;
@@ -392,6 +524,7 @@ __global__ void __launch_bounds__(SG_M3_NCONS + 32, SG_M3_MINB) sg_adj_march3_ke
                 b2s[tid] = (r < r_b && k <= P) ? sg_ldg(a.table2 + r + a.n2 * k) : T(0);
             }
             const int nq = max(0, min(RPT, rg1 - rg0 - r_off));          // rows of this thread in this pass (warp-uniform)
+            const int flags = (store_ok ? 1 : 0) | (r_off == 0 ? 2 : 0) | (blk_par << 3);
 
             T acc[RPT][P + 1];
 #pragma unroll
@@ -400,10 +533,9 @@ __global__ void __launch_bounds__(SG_M3_NCONS + 32, SG_M3_MINB) sg_adj_march3_ke
                 for (int k = 0; k <= P; ++k) acc[q][k] = T(0);
             int cur = s3_first;
 
-            // One control plane of dimension 3 is complete (acc[.][0]): contract it over dimension 2, then over
-            // dimension 1, write the NI1 x S2 partials, slide the window.
+            // One control plane of dimension 3 is complete (acc[.][0]): contract this thread's rows over dimension 2,
+            // push the span partial into the post pipeline, slide the window.  No block-wide barrier.
             auto emit_oldest = [&]() {
-                // (1) span partial over dimension 2: t[k] = sum_q B2[row q, k] * acc[q][0]  -> t4[g][k][col]
                 T t[4] = {T(0), T(0), T(0), T(0)};
 #pragma unroll
                 for (int q = 0; q < RPT; ++q) {
@@ -412,72 +544,7 @@ __global__ void __launch_bounds__(SG_M3_NCONS + 32, SG_M3_MINB) sg_adj_march3_ke
 #pragma unroll
                     for (int k = 0; k <= P; ++k) t[k] = fma(w[k], acc[q][0], t[k]);
                 }
-                sg_m3_consumer_bar();           // the previous emit has finished reading t4 (as span sums) and park
-#pragma unroll
-                for (int k = 0; k < 4; ++k) t4[(g * 4 + k) * CW + col] = t[k];
-                sg_m3_consumer_bar();
-                // (2) control slots: park[slot][col] = sum_{g'+k = slot} t4[g'][k][col]
-                for (int u = tid; u < S2 * CW; u += NCONS) {
-                    const int slot = u / CW, c = u & (CW - 1);
-                    T v = T(0);
-#pragma unroll
-                    for (int gg = 0; gg < G2; ++gg) {
-                        const int k = slot - gg;
-                        if (k >= 0 && k <= P) v += t4[(gg * 4 + k) * CW + c];
-                    }
-                    park[slot * PITCH + c + (c >> 2)] = v;
-                }
-                sg_m3_consumer_bar();
-                T *__restrict__ prow = pcol + row_stride * ((int64_t)(cur - P - 1) + (int64_t)kseg * (P + 1));
-                if (fast_block) {
-                    // (3) per knot span of dimension 1 and slot: A[e] = sum_{j in span} B1[j,e] * park[slot][j]
-                    const bool has_unit = tid < nsp_b * S2;
-                    T A[4] = {T(0), T(0), T(0), T(0)};
-                    if (has_unit) {
-                        const uint32_t xb = park_u + (uint32_t)(uslot * PITCH * sizeof(T));
-                        for (int j = uc0; j < uc1; ++j) {
-                            const uint32_t jsk = (uint32_t)(j + (j >> 2));
-                            T w[4];
-                            sg_lds2(wab_u + jsk * (uint32_t)(2 * sizeof(T)), w[0], w[1]);
-                            sg_lds2(wab_u + (PITCH + jsk) * (uint32_t)(2 * sizeof(T)), w[2], w[3]);
-                            const T x = sg_lds(xb + jsk * (uint32_t)sizeof(T), T(0));
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) A[e] = fma(w[e], x, A[e]);
-                        }
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) t4[(uslot * 4 + e) * NSPMAX + usl] = A[e];   // t4 is free after (2)
-                    }
-                    sg_m3_consumer_bar();
-                    // (4) control indices: out[il][slot] = sum_e A[il - e][slot][e]
-                    auto out_of = [&](int il, int slot) -> T {
-                        T sum = T(0);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int sl = il - e;
-                            if (e <= a.P1 && sl >= 0 && sl < nsp_b) sum += t4[(slot * 4 + e) * NSPMAX + sl];
-                        }
-                        return sum;
-                    };
-#pragma unroll
-                    for (int m = 0; m < MOUT; ++m) {
-                        if (od[m] >> 31) {
-                            const int il = (int)(od[m] & 0xffffu), slot = (int)((od[m] >> 16) & 0x3fffu);
-                            const T v = out_of(il, slot);
-                            if (store_ok) { T *dst = prow + il + (int64_t)a.L1 * slot; *dst = first_pass ? v : *dst + v; }
-                        }
-                    }
-                    for (int om = tid + NCONS * MOUT; om < ni1 * S2; om += NCONS) {
-                        const int il = om % ni1, slot = om / ni1;
-                        const T v = out_of(il, slot);
-                        if (store_ok) { T *dst = prow + il + (int64_t)a.L1 * slot; *dst = first_pass ? v : *dst + v; }
-                    }
-                } else {
-                    for (int om = tid; om < ni1 * S2; om += NCONS) {       // sparse sampling / high degree in dimension 1
-                        const int il = om % ni1, slot = om / ni1;
-                        const T v = gather_slow(il, slot);
-                        if (store_ok) { T *dst = prow + il + (int64_t)a.L1 * slot; *dst = first_pass ? v : *dst + v; }
-                    }
-                }
+                pipeline_step(true, t, col_off + row_stride * (int64_t)(cur - P - 1), b1, flags);
 #pragma unroll
                 for (int q = 0; q < RPT; ++q) {
 #pragma unroll
@@ -537,6 +604,12 @@ __global__ void __launch_bounds__(SG_M3_NCONS + 32, SG_M3_MINB) sg_adj_march3_ke
         // control planes this segment holds: bit kseg of the column's row mask (integer OR: order-independent)
         if (store_ok)
             for (int r = s3_first - P - 1 + tid; r < s3_last; r += NCONS) atomicOr(a.rowmask + colid * a.c3 + r, 1u << kseg);
+    }
+    // drain the post pipeline
+    {
+        const T t0[4] = {T(0), T(0), T(0), T(0)};
+#pragma unroll 1
+        for (int k = 0; k < 3; ++k) pipeline_step(false, t0, 0, 0, 0);
     }
 }
 

@@ -341,8 +341,9 @@ struct SgMarch3Plan {
 static size_t sg_m3_smem_bytes(int elem_size, int P)
 {
     const size_t S2 = SG_M3_G2 + P;
-    return (size_t)elem_size * ((size_t)SG_M3_NS * SG_M3_G2 * SG_M3_RPT * SG_M3_CW + S2 * SG_M3_PITCH + (size_t)SG_M3_G2 * 4 * SG_M3_CW +
-                                (size_t)4 * SG_M3_PITCH + (size_t)SG_M3_G2 * SG_M3_RPT * 4 + (size_t)SG_M3_MAXPL * 4) +
+    return (size_t)elem_size * ((size_t)SG_M3_NS * SG_M3_G2 * SG_M3_RPT * SG_M3_CW + (size_t)3 * SG_M3_G2 * 4 * SG_M3_CW +
+                                3 * S2 * SG_M3_PITCH + 3 * S2 * 4 * SG_M3_NSPMAX + (size_t)8 * SG_M3_PITCH + (size_t)SG_M3_G2 * SG_M3_RPT * 4 +
+                                (size_t)SG_M3_MAXPL * 4) +
            sizeof(int) * SG_M3_MAXPL + 128;
 }
 
@@ -366,7 +367,7 @@ static int sg_m3_workers(int elem_size, int P, size_t smem)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const void *k = elem_size == 4 ? sg_m3_kernel_ptr<float>(P) : sg_m3_kernel_ptr<double>(P);
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, SG_M3_NCONS + 32, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, SG_M3_THREADS, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     return sms * per_sm;
 }
 
@@ -393,7 +394,7 @@ static SgMarch3Plan sg_adjoint_march3_plan(int nin, const int64_t *n_samples, co
     mp.nb1 = (int)((n_samples[0] + SG_M3_CW - 1) / SG_M3_CW);
     mp.tiles2 = (int)((nsp2 + SG_M3_G2 - 1) / SG_M3_G2);
     const int64_t ncols = (int64_t)nout * mp.nb1 * mp.tiles2;
-    if (n_cp[1] > 65535 || n_cp[2] * nout > 65535 || ncols > (1 << 24)) return mp;
+    if (n_cp[1] > 65535 || n_cp[2] * nout > 65535 || ncols > (1 << 24) || mp.tiles2 > SG_M3_MAXTILES) return mp;
     mp.smem = sg_m3_smem_bytes(elem_size, P);
     mp.W = sg_m3_workers(elem_size, P, mp.smem);
     if (mp.W <= 0) return mp;
@@ -472,9 +473,9 @@ static int sg_run_march3(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &s
     if (!sg_m3_make_maps<T>(maps, eval, m.n1, m.n2, m.n3 * a.nout)) return SG_ERR_UNSUPPORTED;
     SG_CUDA(cudaMemsetAsync(m.rowmask, 0, mp.mask_bytes, st));
     switch (mp.P) {
-        case 1: sg_adj_march3_kernel<T, 1><<<mp.W, SG_M3_NCONS + 32, mp.smem, st>>>(m, maps); break;
-        case 2: sg_adj_march3_kernel<T, 2><<<mp.W, SG_M3_NCONS + 32, mp.smem, st>>>(m, maps); break;
-        default: sg_adj_march3_kernel<T, 3><<<mp.W, SG_M3_NCONS + 32, mp.smem, st>>>(m, maps); break;
+        case 1: sg_adj_march3_kernel<T, 1><<<mp.W, SG_M3_THREADS, mp.smem, st>>>(m, maps); break;
+        case 2: sg_adj_march3_kernel<T, 2><<<mp.W, SG_M3_THREADS, mp.smem, st>>>(m, maps); break;
+        default: sg_adj_march3_kernel<T, 3><<<mp.W, SG_M3_THREADS, mp.smem, st>>>(m, maps); break;
     }
     dim3 cgrid(sg_blocks(m.c1, 128), (unsigned)m.c2, (unsigned)(m.c3 * a.nout));
     sg_adj_combine3_kernel<T><<<cgrid, 128, 0, st>>>(cp, m.part, m.rowmask, hdr, m.index1, m.n1, m.c1, m.c2, m.c3, m.P1, mp.P, SG_M3_G2,
