@@ -1,0 +1,175 @@
+// sg_adjoint_post2.cuh -- second half of the 3-D double-march adjoint (K4, src/adjoint.jl:1-83) as ONE kernel:
+// halo combine of the tile/chunk partials of dimensions 2 and 3 AND the contraction of dimension 1.
+//
+//   cp[i1, i2, i3, o] = sum_{j1 in range(i1)} B1[j1, i1 - base(j1)] * R[j1, i2, i3, o]
+//   R[j1, i2, i3, o]  = sum over the (<= 2) tiles of dimension 2 and the chunks of dimension 3 that hold (i2, i3)
+//                       of the partials written by sg_adj_march2(_tma)_kernel
+//
+// A CTA owns a block of 128 control indices i1, the G2 control rows i2 of one tile and one control plane i3.  It sums
+// the partial rows that cover its G2 rows (slots 0..G2-1 of its own tile, the P halo slots of the previous tile, each
+// from every chunk holding i3) with coalesced streaming loads into a shared-memory row buffer -- R never goes to
+// HBM -- and then every thread gathers its control index over the samples of its support with the basis weights of
+// dimension 1.  The order of every sum is fixed: deterministic, no atomics.
+// The sample range of the i1 block is walked in pieces of SG_POST2_JMAX samples, so any n1 works.
+// Replaces sg_adj_combine2_scan_kernel + sg_adj_first_dim_*_kernel (102 us -> one pass over the partials on C3).
+#pragma once
+#include <type_traits>
+#include "sg_fast_adjoint.cuh"
+
+#define SG_POST2_JMAX 512
+#define SG_POST2_RMAX 20          // gather weights kept in registers per control index
+#define SG_POST2_PITCH (SG_POST2_JMAX + SG_POST2_JMAX / 4 + 4)   // skewed row: sample jj lives at jj + (jj >> 2)
+
+// grid = ((tiles2 + 1) * ceil(c1 / 128), c3, nout); requires G2 >= P (only neighbouring tiles overlap)
+template <typename T, int P, int G2>
+__global__ void __launch_bounds__(128, 5) sg_adj_post2_kernel(T *__restrict__ cp, const T *__restrict__ Pp, const T *__restrict__ table1,
+                                                           const int32_t *__restrict__ index1, const int32_t *__restrict__ start1,
+                                                           const SgAdjointHeader *hdr, int64_t n1, int64_t c1, int64_t c2, int64_t c3, int P1,
+                                                           int tiles2, int G3, int chunks3, int path)
+{
+    constexpr int S = G2 + P;
+    constexpr int JMAX = SG_POST2_JMAX;
+    __shared__ T rows[G2][SG_POST2_PITCH];
+    const int tid = threadIdx.x;
+    const int t = (int)(blockIdx.x % (unsigned)(tiles2 + 1));          // tile of dimension 2 (tiles2 = the last tile's halo rows)
+    const int64_t ib = blockIdx.x / (unsigned)(tiles2 + 1);            // block of control indices of dimension 1
+    const int64_t i3 = (int64_t)blockIdx.y + 1;                         // 1-based control index of dimension 3
+    const int64_t o = blockIdx.z;
+    const int64_t i2_0 = (int64_t)t * G2;                               // 0-based control row of slot 0
+    if (i2_0 >= c2) return;
+    const int sf = hdr->span_first[2], sl = hdr->span_last[2];
+    // This kernel writes EVERY control point (no memset before the pipeline): zeros outside the support of this (slab
+    // of the) grid, and zeros everywhere if the prep kernel flagged non-monotone spans (the scatter kernel accumulates).
+    if (!sg_adj_path_active(hdr, path) || i3 < sf - P || i3 > sl) {
+        const int64_t iz = ib * 128 + tid;
+        if (iz < c1) {
+            T *__restrict__ out = cp + iz + c1 * (i2_0 + c2 * ((i3 - 1) + c3 * o));
+#pragma unroll
+            for (int q = 0; q < G2; ++q)
+                if (i2_0 + q < c2) out[c1 * q] = T(0);
+        }
+        return;
+    }
+    const int rows3 = G3 + P;
+    // the (<= 2, because G3 >= P) chunks of dimension 3 whose written rows contain i3
+    int64_t off0 = 0, off1 = 0;
+    int nc = 0;
+    {
+        const int64_t c_hi = min((i3 - 1) / G3, (int64_t)chunks3 - 1), c_lo = max((int64_t)0, (i3 - P - 1 + G3) / G3 - 1);
+        for (int64_t c = c_lo; c <= c_hi; ++c) {
+            const int64_t l3 = i3 - (c * G3 + 1);
+            if (l3 < 0 || l3 >= rows3) continue;
+            const int64_t cs_lo = max((int64_t)(P + 1 + c * G3), (int64_t)sf);
+            const int64_t cs_hi = min(min((int64_t)(P + 1 + c * G3 + G3), c3 + 1), (int64_t)sl + 1);
+            if (cs_lo >= cs_hi || i3 < cs_lo - P || i3 > cs_hi - 1) continue;   // rows this chunk really wrote
+            // slot 0 of tile t in row l3 of chunk c
+            const int64_t off = n1 * (int64_t)S * (t + (int64_t)tiles2 * (l3 + (int64_t)rows3 * (c + (int64_t)chunks3 * o)));
+            if (nc == 0) off0 = off; else if (nc == 1) off1 = off;
+            ++nc;
+        }
+        nc = min(nc, 2);
+    }
+    const bool own = t < tiles2, prev = t >= 1;                          // CTA-uniform sources
+
+    // this thread's control index and its sample range; the block's sample range
+    const int64_t i1 = ib * 128 + tid;                                   // 0-based
+    const bool valid = i1 < c1;
+    int64_t lo = 0, hi = 0;
+    if (valid) {
+        const int64_t i = i1 + 1;
+        const int64_t s0 = i > P1 + 1 ? i : P1 + 1;
+        const int64_t s1 = i + P1 < c1 ? i + P1 : c1;
+        lo = start1[s0]; hi = start1[s1 + 1];
+    }
+    int64_t jb_lo, jb_hi;
+    {
+        const int64_t ia = ib * 128 + 1, iz = min(ib * 128 + 128, c1);
+        jb_lo = start1[ia > P1 + 1 ? ia : P1 + 1];
+        jb_hi = start1[(iz + P1 < c1 ? iz + P1 : c1) + 1];
+    }
+    // Gather weights of this control index in registers (they do not depend on the row): two rounds of independent
+    // loads (span indices, then table entries) instead of a dependent chain per sample.  Ranges longer than RMAX, or a
+    // block range longer than one piece, take the look-up loop below.
+    constexpr int RMAX = SG_POST2_RMAX;
+    const int len_i = (int)(hi - lo);
+    const bool regw = __syncthreads_and((!valid || len_i <= RMAX) ? 1 : 0) && (jb_hi - jb_lo) <= JMAX;   // CTA-uniform
+    T w[RMAX];
+    if (regw) {
+        int kk[RMAX];
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) kk[r] = r < len_i ? (int)(i1 + 1 - sg_ldg(index1 + lo + r) + P1) : 0;
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) w[r] = r < len_i ? sg_ldg(table1 + lo + r + n1 * kk[r]) : T(0);
+    }
+    T acc[G2];
+#pragma unroll
+    for (int q = 0; q < G2; ++q) acc[q] = T(0);
+
+    for (int64_t jc = jb_lo; jc < jb_hi; jc += JMAX) {
+        const int len = (int)min((int64_t)JMAX, jb_hi - jc);
+        __syncthreads();                                                // the previous piece has been consumed
+        // Every load of a sample column is issued before the first use (predicates are CTA-uniform compile-time
+        // constants inside each instantiation): 2 columns x up to 2 chunks x (G2 + P) rows in flight per thread.
+        auto load_piece = [&](auto OWN, auto PREV, auto TWO) {
+            constexpr bool own_c = decltype(OWN)::value, prev_c = decltype(PREV)::value, two_c = decltype(TWO)::value;
+#pragma unroll 2
+            for (int jj = tid; jj < len; jj += 128) {
+                const T *__restrict__ p0 = Pp + jc + jj + off0;
+                const T *__restrict__ p1 = Pp + jc + jj + off1;
+                T ra[G2], rb[P], sa[G2], sb[P];
+#pragma unroll
+                for (int q = 0; q < G2; ++q) { ra[q] = own_c ? __ldcs(p0 + n1 * q) : T(0); sa[q] = (own_c && two_c) ? __ldcs(p1 + n1 * q) : T(0); }
+#pragma unroll
+                for (int q = 0; q < P; ++q) {                           // slot G2 + q of tile t - 1
+                    rb[q] = prev_c ? __ldcs(p0 - n1 * (S - G2 - q)) : T(0);
+                    sb[q] = (prev_c && two_c) ? __ldcs(p1 - n1 * (S - G2 - q)) : T(0);
+                }
+                const int js = jj + (jj >> 2);
+#pragma unroll
+                for (int q = 0; q < G2; ++q) {
+                    T v = ra[q] + sa[q];
+                    if (q < P) v += rb[q] + sb[q];
+                    rows[q][js] = v;
+                }
+            }
+        };
+        using TT = std::true_type;
+        using FF = std::false_type;
+        if (nc == 2) {
+            if (own && prev) load_piece(TT{}, TT{}, TT{}); else if (own) load_piece(TT{}, FF{}, TT{}); else load_piece(FF{}, TT{}, TT{});
+        } else if (nc == 1) {
+            if (own && prev) load_piece(TT{}, TT{}, FF{}); else if (own) load_piece(TT{}, FF{}, FF{}); else load_piece(FF{}, TT{}, FF{});
+        } else {
+            load_piece(FF{}, FF{}, FF{});                               // no chunk wrote this control plane: zeros
+        }
+        __syncthreads();
+        if (regw) {
+            if (valid) {
+                const int j0 = (int)(lo - jc);                          // one piece: jc == jb_lo <= lo
+#pragma unroll
+                for (int r = 0; r < RMAX; ++r) {
+                    if (r < len_i) {
+                        const int jj = j0 + r, js = jj + (jj >> 2);
+#pragma unroll
+                        for (int q = 0; q < G2; ++q) acc[q] = fma(w[r], rows[q][js], acc[q]);
+                    }
+                }
+            }
+        } else if (valid) {
+            const int64_t ja = max(lo, jc), jz = min(hi, jc + len);
+            for (int64_t j = ja; j < jz; ++j) {
+                const int k = (int)(i1 + 1 - sg_ldg(index1 + j) + P1);
+                const T wj = sg_ldg(table1 + j + n1 * k);
+                const int jj = (int)(j - jc), js = jj + (jj >> 2);
+#pragma unroll
+                for (int q = 0; q < G2; ++q) acc[q] = fma(wj, rows[q][js], acc[q]);
+            }
+        }
+    }
+    if (valid) {
+        T *__restrict__ out = cp + i1 + c1 * (i2_0 + c2 * ((i3 - 1) + c3 * o));
+#pragma unroll
+        for (int q = 0; q < G2; ++q)
+            if (i2_0 + q < c2) out[c1 * q] = acc[q];
+    }
+}

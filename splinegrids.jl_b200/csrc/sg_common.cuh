@@ -91,7 +91,7 @@ static inline int sg_fill_grid_args(SgGridArgs<T> &a, int nin, const int64_t *n_
 // Adjoint workspace header (first 256 bytes of the workspace)
 struct SgAdjointHeader {
     int nonmonotone;  // set to 1 by the prep kernel if any dimension's span indices decrease
-    int fused_bad;    // (unused) kept for layout stability
+    int m2_skipped;   // set by the TMA-fed double march when it leaves a tile to the register kernel (complement pass)
     int span_first[SG_MAX_DIMS];   // span of the first / last sample of every dimension (1-based), written by the
     int span_last[SG_MAX_DIMS];    // prep kernel: the control indices a (slab of a) grid can touch are [first-p, last]
     int pad[62 - 2 * SG_MAX_DIMS];

@@ -8,6 +8,7 @@
 #include "sg_fast.cuh"
 #include "sg_fast_adjoint.cuh"
 #include "sg_adjoint_march3.cuh"
+#include "sg_adjoint_post2.cuh"
 #include "sg_fast_eval.cuh"
 
 static int sg_env_int(const char *name, int dflt)
@@ -300,7 +301,9 @@ static SgMarch2Plan sg_adjoint_march2_plan(int nin, const int64_t *n_samples, co
     // of a sharded grid touches few control planes: the chunked multi-pass pipeline is better there)
     const int mode = sg_env_int("SG_ADJ_MARCH2", -1);
     if (rational || nin != 3 || mode == 0) return mp;
-    if (mode < 0 && n_samples[2] < 2 * (n_cp[2] - degree[2])) return mp;
+    // the slab of a sharded grid has few sample planes but the same density as the full grid (its samples sit in a few
+    // consecutive spans; chunks without samples exit at once), so only very thin inputs go to the multi-pass pipeline
+    if (mode < 0 && n_samples[2] < 16) return mp;
     const int P = degree[1];
     if (degree[2] != P || P < 1 || P > 3) return mp;
     if (n_samples[0] < 128) return mp;
@@ -311,7 +314,7 @@ static SgMarch2Plan sg_adjoint_march2_plan(int nin, const int64_t *n_samples, co
     const int64_t base = n_samples[0] * mp.tiles2 * nout;
     const int64_t chunks_needed = std::max<int64_t>(1, (294912 + base - 1) / base);   // ~300K threads (G3 ~ 7 on C3) measured best
     const int64_t act_spans = std::min<int64_t>(nsp3, n_samples[2]);
-    int64_t G3 = std::max<int64_t>(2, act_spans / chunks_needed);
+    int64_t G3 = std::max<int64_t>(std::max(2, P), act_spans / chunks_needed);   // G3 >= P: only neighbouring chunks overlap
     const int forced = sg_env_int("SG_ADJ_M2_G3", 0);
     if (forced > 0) G3 = forced;
     G3 = std::min<int64_t>(G3, nsp3);
@@ -551,19 +554,27 @@ static int sg_launch_march2(const SgAdj2Args<T> &m, int nout, cudaStream_t st)
     // TMA-fed ring: bulk copies need 16-byte aligned rows; rows per tile are data dependent, so the expected count must
     // fit the ring (tiles that do not are skipped by the TMA kernel and done by the register kernel right after)
     const bool tma_ok = sg_env_int("SG_ADJ_M2_TMA", 1) && (m.n1 * sizeof(T)) % 16 == 0 && reinterpret_cast<uintptr_t>(m.X) % 16 == 0 &&
-                        (double)m.n2 / (double)std::max<int64_t>(1, m.c2 - P) * SG_M2_G2 <= SG_M2_RTMAX - 2;
+                        (double)m.n2 / (double)std::max<int64_t>(1, m.c2 - P) * SG_M2_G2 <= SG_M2_RTMAX - 2 &&
+                        (double)m.n1 * (SG_M2_G2 + P) * m.tiles2 * (m.G3 + P) * m.chunks3 * nout < 4.0e9;   // 32-bit partial offsets
     if (tma_ok) {
         auto kern = sg_adj_march2_tma_kernel<T, P, SG_M2_G2, SG_M2_RTMAX, SG_M2_NS>;
         const size_t smem = sizeof(T) * SG_M2_NS * SG_M2_RTMAX * 128;
         SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, 160, smem, st>>>(m);                                   // 4 consumer warps + 1 producer warp
-        sg_adj_march2_kernel<T, P, SG_M2_G2, SG_M2_RS><<<grid, 128, 0, st>>>(m, SG_M2_RTMAX);   // tiles with more rows (normally none)
+        // tiles with more rows than the ring holds (normally none: one idle launch)
+        sg_adj_march2_complement_kernel<T, P, SG_M2_G2, SG_M2_RS><<<148 * 4, 128, 0, st>>>(m, SG_M2_RTMAX, grid.x, grid.y, grid.z);
         g_sg_launches.fetch_add(2);
         return SG_OK;
     }
     sg_adj_march2_kernel<T, P, SG_M2_G2, SG_M2_RS><<<grid, 128, 0, st>>>(m, 0);
     g_sg_launches.fetch_add(1);
     return SG_OK;
+}
+
+// halo combine + dimension-1 contraction in one kernel (also zero-fills cp where nothing is written)
+static bool sg_m2_post_eligible(const SgMarch2Plan &mp, int P, int nout)
+{
+    return sg_env_int("SG_ADJ_M2_POST", 1) && mp.ok && mp.G3 >= P && SG_M2_G2 >= P && nout <= 65535;
 }
 
 template <typename T>
@@ -585,6 +596,18 @@ static int sg_run_march2(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &s
         default: lrc = sg_launch_march2<T, 3>(m, a.nout, st); break;
     }
     if (lrc != SG_OK) return lrc;
+    if (sg_m2_post_eligible(mp, P, a.nout)) {
+        // halo combine + contraction of dimension 1 in one kernel (sg_adjoint_post2.cuh): the partials are read once and
+        // the (n1, c2, c3) intermediate never goes to HBM
+        dim3 pgrid((unsigned)((mp.tiles2 + 1) * sg_blocks(a.n_cp[0], 128)), (unsigned)m.c3, (unsigned)a.nout);
+        switch (P) {
+            case 1: sg_adj_post2_kernel<T, 1, SG_M2_G2><<<pgrid, 128, 0, st>>>(cp, part, a.table[0], a.index[0], ss.start[0], hdr, m.n1, a.n_cp[0], m.c2, m.c3, a.degree[0], mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS); break;
+            case 2: sg_adj_post2_kernel<T, 2, SG_M2_G2><<<pgrid, 128, 0, st>>>(cp, part, a.table[0], a.index[0], ss.start[0], hdr, m.n1, a.n_cp[0], m.c2, m.c3, a.degree[0], mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS); break;
+            default: sg_adj_post2_kernel<T, 3, SG_M2_G2><<<pgrid, 128, 0, st>>>(cp, part, a.table[0], a.index[0], ss.start[0], hdr, m.n1, a.n_cp[0], m.c2, m.c3, a.degree[0], mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS); break;
+        }
+        g_sg_launches.fetch_add(1);
+        return SG_OK;
+    }
     if (sg_env_int("SG_ADJ_M2_SCAN", 1) && mp.G3 >= P && a.nout <= 65535) {
         dim3 sgrid((unsigned)((m.n1 + 127) / 128), (unsigned)m.c3, (unsigned)a.nout);
         switch (P) {
@@ -639,11 +662,11 @@ int sg_evaluate_adjoint_fast(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T
     if (m3.ok && reinterpret_cast<uintptr_t>(eval) % 16 != 0) m3.ok = false;
     // zero fill (src/adjoint.jl:61): needed only if the prep kernel flags non-monotone spans (scatter path); the
     // single-pass pipeline's combine kernel does it itself
-    if (!m3.ok) SG_CUDA(cudaMemsetAsync(cp, 0, (size_t)a.cp_total * a.nout * sizeof(T), st));
-
     SgFusedPlan fp = sg_adjoint_fused_plan(a.nin, a.n_samples, a.n_cp, a.nout, a.degree, (int)sizeof(T), rational);
     if (fp.ok && reinterpret_cast<uintptr_t>(eval) % 16 != 0) fp.ok = false;
     const SgMarch2Plan mp = sg_adjoint_march2_plan(a.nin, a.n_samples, a.n_cp, a.nout, a.degree, (int)sizeof(T), rational);
+    const bool self_zero = m3.ok || (!fp.ok && sg_m2_post_eligible(mp, a.degree[1], a.nout));   // the last kernel writes every cp
+    if (!self_zero) SG_CUDA(cudaMemsetAsync(cp, 0, (size_t)a.cp_total * a.nout * sizeof(T), st));
     int rc;
     if (m3.ok) {
         rc = sg_run_march3<T>(cp, a, ss, hdr, eval, m3, ws, st);
@@ -660,7 +683,7 @@ int sg_evaluate_adjoint_fast(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T
     }
     if (rc != SG_OK) return rc;
     // non-monotone span indices (decided on device): the reference's atomic scatter
-    const unsigned sblocks = (unsigned)std::min<int64_t>(sg_blocks(a.n_total, 256), 148 * 16);   // fallback: fixed small grid
+    const unsigned sblocks = (unsigned)std::min<int64_t>(sg_blocks(a.n_total, 256), 148 * 4);   // fallback: fixed small grid
     if (rational)
         sg_adjoint_scatter_kernel<T, true><<<sblocks, 256, 0, st>>>(cp, a, hdr, eval, weights);
     else

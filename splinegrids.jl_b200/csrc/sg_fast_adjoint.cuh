@@ -703,6 +703,7 @@ __global__ void __launch_bounds__(128) sg_adj_tile_combine_kernel(T *__restrict_
 // kernel).  For C3 the pass writes ~130 MB instead of the 268 + 67 MB of the two separate passes.
 // Rows of a span are processed RS at a time (any number of samples per span works).
 // =============================================================================================
+#define SG_M2_FAST_ROWS 5      // row slots per knot span in the TMA-fed kernel's straight-line contraction
 template <typename T>
 struct SgAdj2Args {
     const T *X;                 // eval (n1, n2, n3, nout)
@@ -710,16 +711,16 @@ struct SgAdj2Args {
     const T *table2, *table3;   // (n2, P+1), (n3, P+1) selected derivative slices
     const int32_t *index3;
     const int32_t *start2, *start3;   // span_start arrays
-    const SgAdjointHeader *hdr;
+    SgAdjointHeader *hdr;
     int64_t n1, n2, n3, c2, c3;
     int tiles2, G3, chunks3;
     int path;
 };
 
 template <typename T, int P, int G2, int RS>
-__global__ void __launch_bounds__(128) sg_adj_march2_kernel(const __grid_constant__ SgAdj2Args<T> a, int only_tiles_above_rows)
+__device__ __forceinline__ void sg_adj_march2_body(const SgAdj2Args<T> &a, int only_tiles_above_rows, const unsigned bx, const unsigned by,
+                                                   const unsigned bz)
 {
-    if (!sg_adj_path_active(a.hdr, a.path)) return;
     constexpr int S = G2 + P;
     constexpr int PIECE = 32;
     __shared__ __align__(16) T b3s[PIECE * (P + 1)];
@@ -728,21 +729,27 @@ __global__ void __launch_bounds__(128) sg_adj_march2_kernel(const __grid_constan
     constexpr int B2ROWS = G2 * RS * 2;                                 // table rows of dimension 2 staged per tile
     __shared__ __align__(16) T b2s[B2ROWS * (P + 1)];
 
-    const int64_t j1 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int tile2 = blockIdx.y;
-    const int c3k = blockIdx.z % a.chunks3;
-    const int64_t o = blockIdx.z / a.chunks3;
+    const int64_t j1 = (int64_t)bx * blockDim.x + threadIdx.x;
+    const int tile2 = by;
+    const int c3k = bz % a.chunks3;
+    const int64_t o = bz / a.chunks3;
     const bool active = j1 < a.n1;
 
     // spans of dimension 2 in this tile: [s2_lo, s2_lo + G2) clipped; rows of span g: [row0[g], row0[g+1])
     const int s2_lo = P + 1 + tile2 * G2;
+    __syncthreads();                                                   // (persistent caller) the previous tile is done with row0
     if (threadIdx.x <= G2) {
         const int sidx = (int)min((int64_t)s2_lo + threadIdx.x, a.c2 + 1);
         row0[threadIdx.x] = a.start2[sidx];
     }
     __syncthreads();
     // complement of the TMA-fed kernel: only the tiles it skipped (more rows than its ring holds)
-    if (only_tiles_above_rows > 0 && row0[G2] - row0[0] <= only_tiles_above_rows) return;   // block-uniform
+    if (only_tiles_above_rows > 0) {                                   // block-uniform: exactly the tiles the TMA kernel skipped
+        bool tma_did_it = row0[G2] - row0[0] <= only_tiles_above_rows;
+#pragma unroll
+        for (int g = 0; g < G2; ++g) tma_did_it = tma_did_it && row0[g + 1] - row0[g] <= SG_M2_FAST_ROWS;
+        if (tma_did_it) return;
+    }
     {   // table rows of the tile (rows are contiguous: [row0[0], row0[G2])); rows beyond B2ROWS use global look-ups
         const int r_first = row0[0], n_rows = min(row0[G2] - row0[0], B2ROWS);
         for (int q = threadIdx.x; q < n_rows * (P + 1); q += blockDim.x) {
@@ -857,6 +864,26 @@ __global__ void __launch_bounds__(128) sg_adj_march2_kernel(const __grid_constan
     }
 }
 
+template <typename T, int P, int G2, int RS>
+__global__ void __launch_bounds__(128) sg_adj_march2_kernel(const __grid_constant__ SgAdj2Args<T> a, int only_tiles_above_rows)
+{
+    if (!sg_adj_path_active(a.hdr, a.path)) return;
+    sg_adj_march2_body<T, P, G2, RS>(a, only_tiles_above_rows, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// Complement of the TMA-fed kernel: a small persistent grid that walks the (column block, tile, chunk) space and does
+// the tiles the TMA kernel skipped (more rows than its ring holds).  Normally there are none: the TMA kernel raises
+// hdr->m2_skipped only when it skips a tile, so this kernel costs one launch and exits.
+template <typename T, int P, int G2, int RS>
+__global__ void __launch_bounds__(128) sg_adj_march2_complement_kernel(const __grid_constant__ SgAdj2Args<T> a, int only_tiles_above_rows,
+                                                                       unsigned nbx, unsigned nby, unsigned nbz)
+{
+    if (!sg_adj_path_active(a.hdr, a.path) || a.hdr->m2_skipped == 0) return;
+    const uint64_t total = (uint64_t)nbx * nby * nbz;
+    for (uint64_t vb = blockIdx.x; vb < total; vb += gridDim.x)
+        sg_adj_march2_body<T, P, G2, RS>(a, only_tiles_above_rows, (unsigned)(vb % nbx), (unsigned)((vb / nbx) % nby), (unsigned)(vb / ((uint64_t)nbx * nby)));
+}
+
 // R'[j1, i2, i3, o] = sum over tiles of dim 2 covering i2 and chunks of dim 3 covering i3 of the partials.
 // grid = (ceil(n1/128), ceil(c2/SG_COMBINE_ROWS), c3*nout)
 template <typename T>
@@ -929,7 +956,8 @@ __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_
     __shared__ __align__(16) T b3s[MAXPL * (P + 1)];
     __shared__ int s3s[MAXPL];
     __shared__ int row0[G2 + 1];
-    __shared__ __align__(16) T b2s[RTMAX * (P + 1)];
+    constexpr int RS5 = SG_M2_FAST_ROWS;                                // row slots per span of the straight-line contraction
+    __shared__ __align__(16) T b2pad[G2 * RS5 * (P + 1)];               // [span g][row q][k], zero for absent rows
     __shared__ __align__(8) uint64_t full[NS];
     __shared__ __align__(8) uint64_t empty[NS];
 
@@ -947,12 +975,32 @@ __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_
     if (tid <= G2) row0[tid] = a.start2[(int)min((int64_t)s2_lo + tid, a.c2 + 1)];
     if (tid == 0) {
 #pragma unroll
-        for (int q = 0; q < NS; ++q) { sg_mbar_init(&full[q], 1); sg_mbar_init(&empty[q], CW); }
+        for (int q = 0; q < NS; ++q) { sg_mbar_init(&full[q], 1); sg_mbar_init(&empty[q], CW / 32); }   // one arrival per consumer warp
     }
     __syncthreads();
     const int r_first = row0[0], n_rows = row0[G2] - row0[0];
-    if (n_rows > RTMAX) return;                                         // block-uniform: the register kernel takes this tile
-    for (int q = tid; q < n_rows * (P + 1); q += blockDim.x) b2s[q] = sg_ldg(a.table2 + (r_first + q / (P + 1)) + a.n2 * (q % (P + 1)));
+    // Straight-line contraction of dimension 2 (no data-dependent loops, no predicates): a ring stage holds G2 x RS5
+    // fixed row slots, slot (g, q) = q-th row of span g of the tile.  The producer copies every present row into its
+    // slot; absent slots are zeroed once here and never written again, and their weights are zero.  Tiles with a span
+    // of more than RS5 rows are left to the register kernel (complement pass).  All CTA-uniform.
+    static_assert(G2 * SG_M2_FAST_ROWS <= RTMAX, "ring stage holds G2 x RS5 row slots");
+    bool fastrows = true;
+#pragma unroll
+    for (int g = 0; g < G2; ++g) fastrows = fastrows && row0[g + 1] - row0[g] <= RS5;
+    if (!fastrows) {
+        if (tid == 0) a.hdr->m2_skipped = 1;
+        return;
+    }
+    if (!is_producer) {
+        for (int q = tid; q < G2 * RS5 * (P + 1); q += CW) {
+            const int k = q % (P + 1), gq = q / (P + 1), g = gq / RS5, qq = gq % RS5;
+            b2pad[q] = qq < row0[g + 1] - row0[g] ? sg_ldg(a.table2 + (row0[g] + qq) + a.n2 * k) : T(0);
+        }
+        for (int sl = 0; sl < NS * G2 * RS5; ++sl) {                    // absent slots of every stage (never touched by the copies)
+            const int gq = sl % (G2 * RS5), g = gq / RS5, qq = gq % RS5;
+            if (qq >= row0[g + 1] - row0[g]) xs[(size_t)(sl / (G2 * RS5)) * RTMAX * CW + (size_t)gq * CW + tid] = T(0);
+        }
+    }
 
     const int s3_lo0 = P + 1 + c3k * a.G3;
     const int s3_hi0 = (int)min((int64_t)s3_lo0 + a.G3, a.c3 + 1);
@@ -972,64 +1020,75 @@ __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_
 
     const int64_t plane = a.n1 * a.n2;
     const T *__restrict__ xtile = a.X + j1_0 + a.n1 * (int64_t)r_first + plane * (a.n3 * o + j3_lo);
-    const int64_t y_slot = a.n1;
-    const int64_t y_row3 = a.n1 * (int64_t)S * a.tiles2;
-    T *__restrict__ yp = a.Y + j1 + a.n1 * ((int64_t)S * tile2) + y_row3 * ((int64_t)(s3_lo - s3_lo0) + (int64_t)rows3 * (c3k + (int64_t)a.chunks3 * o));
+    // 32-bit element offsets into the partials (the host checks that they fit): fewer live registers in the plane loop
+    const unsigned y_slot = (unsigned)a.n1;
+    const unsigned y_row3 = (unsigned)(a.n1 * (int64_t)S * a.tiles2);
+    unsigned yoff = (unsigned)(j1 + a.n1 * ((int64_t)S * tile2) + (int64_t)y_row3 * ((int64_t)(s3_lo - s3_lo0) + (int64_t)rows3 * (c3k + (int64_t)a.chunks3 * o)));
+    T *__restrict__ const ybase = a.Y;
     const unsigned row_bytes = (unsigned)(ncols * sizeof(T));
 
     auto emit_oldest = [&]() {
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            __stcs(yp + y_slot * s, acc3[s][0]);
+            __stcs(ybase + (yoff + y_slot * s), acc3[s][0]);
 #pragma unroll
             for (int k = 0; k < P; ++k) acc3[s][k] = acc3[s][k + 1];
             acc3[s][P] = T(0);
         }
-        yp += y_row3;
+        yoff += y_row3;
         ++cur;
     };
 
+    int st = 0;                                                         // ring stage / phase of the next plane (producer and
+    unsigned ph = 0;                                                    // consumers each keep their own running copy)
+    if (is_producer) {
+        // The producer starts feeding the ring at once and runs through the whole chunk on its own; it never meets the
+        // consumers at a block-wide barrier (they stage their tables behind a named barrier of their own).
+        if (tid == CW && n_rows > 0) {                                  // one elected lane
+            for (int p = 0; p < np_total; ++p) {
+                if (p >= NS) sg_mbar_wait(&empty[st], ph ^ 1u);         // every consumer warp has read the previous plane in this stage
+                sg_mbar_expect_tx(&full[st], row_bytes * (unsigned)n_rows);
+                const T *src = xtile + plane * (int64_t)p;
+                T *dst = xs + (size_t)st * RTMAX * CW;
+#pragma unroll
+                for (int g = 0; g < G2; ++g) {
+                    const int ra = row0[g] - r_first, rb = row0[g + 1] - r_first;
+                    for (int r = ra; r < rb; ++r) sg_bulk_g2s(dst + (g * RS5 + (r - ra)) * CW, src + a.n1 * (int64_t)r, row_bytes, &full[st]);
+                }
+                if (++st == NS) { st = 0; ph ^= 1u; }
+            }
+        }
+        return;
+    }
     for (int p0 = 0; p0 < np_total; p0 += MAXPL) {
         const int p1 = min(p0 + MAXPL, np_total);
-        __syncthreads();                                                // consumers are done with the previous piece's tables
-        for (int s = tid; s < p1 - p0; s += blockDim.x) {
+        asm volatile("bar.sync 1, %0;" ::"n"(CW) : "memory");           // consumers are done with the previous piece's tables
+        for (int s = tid; s < p1 - p0; s += CW) {
             s3s[s] = sg_ldg(a.index3 + j3_lo + p0 + s);
 #pragma unroll
             for (int k = 0; k <= P; ++k) b3s[s * (P + 1) + k] = sg_ldg(a.table3 + j3_lo + p0 + s + a.n3 * k);
         }
-        __syncthreads();
-        if (is_producer) {
-            if (tid == CW && n_rows > 0) {                              // one elected lane feeds the ring
-                for (int p = p0; p < p1; ++p) {
-                    const int st = p % NS, k = p / NS;
-                    if (k > 0) sg_mbar_wait(&empty[st], (unsigned)((k - 1) & 1));   // every consumer has read the previous plane in this stage
-                    sg_mbar_expect_tx(&full[st], row_bytes * (unsigned)n_rows);
-                    const T *src = xtile + plane * (int64_t)p;
-                    T *dst = xs + (size_t)st * RTMAX * CW;
-                    for (int r = 0; r < n_rows; ++r) sg_bulk_g2s(dst + r * CW, src + a.n1 * (int64_t)r, row_bytes, &full[st]);
-                }
-            }
-            continue;
-        }
+        asm volatile("bar.sync 1, %0;" ::"n"(CW) : "memory");           // (also covers the dimension-2 weights staged above)
         for (int p = p0; p < p1; ++p) {
-            const int st = p % NS;
             T T2[S];
 #pragma unroll
             for (int q = 0; q < S; ++q) T2[q] = T(0);
             if (n_rows > 0) {
-                sg_mbar_wait(&full[st], (unsigned)((p / NS) & 1));
+                sg_mbar_wait(&full[st], ph);
                 const T *__restrict__ xst = xs + (size_t)st * RTMAX * CW + tid;
                 // ---- contract the tile's rows over dimension 2 (values come from the shared-memory ring)
 #pragma unroll
                 for (int g = 0; g < G2; ++g) {
-                    const int r_lo = row0[g] - r_first, r_hi = row0[g + 1] - r_first;
-                    for (int r = r_lo; r < r_hi; ++r) {
-                        const T x = xst[r * CW];
 #pragma unroll
-                        for (int k = 0; k <= P; ++k) T2[g + k] = fma(b2s[r * (P + 1) + k], x, T2[g + k]);
+                    for (int q = 0; q < RS5; ++q) {
+                        const T x = xst[(g * RS5 + q) * CW];
+#pragma unroll
+                        for (int k = 0; k <= P; ++k) T2[g + k] = fma(b2pad[(g * RS5 + q) * (P + 1) + k], x, T2[g + k]);
                     }
                 }
-                sg_mbar_arrive(&empty[st]);                             // this thread no longer needs the stage
+                __syncwarp();
+                if ((tid & 31) == 0) sg_mbar_arrive(&empty[st]);        // this warp no longer needs the stage
+                if (++st == NS) { st = 0; ph ^= 1u; }
             }
             if (!active) continue;
             // ---- march dimension 3
@@ -1052,7 +1111,7 @@ __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_
 #pragma unroll
     for (int k = 0; k < P; ++k) {
 #pragma unroll
-        for (int s = 0; s < S; ++s) __stcs(yp + y_slot * s + y_row3 * k, acc3[s][k]);
+        for (int s = 0; s < S; ++s) __stcs(ybase + (yoff + y_slot * s + y_row3 * k), acc3[s][k]);
     }
 }
 

@@ -229,6 +229,44 @@ def test_optin_adjoint_pipelines_vs_oracle(S, case, env, variant, monkeypatch):
     assert max_rel_err(S.to_numpy(g), gref) <= 10 * _tol(ft)
 
 
+POST2_CASES = [
+    # n_cp, degree, n_samples, nout, float type: shapes that exercise sg_adj_post2_kernel (halo combine + dimension 1)
+    ((20, 11, 9), (3, 3, 3), (1400, 40, 20), 1, "Float64"),      # sample range of an i1 block > SG_POST2_JMAX: three pieces
+    ((300, 9, 8), (3, 2, 2), (640, 30, 24), 2, "Float64"),       # three blocks of control indices, Nout 2
+    ((150, 14, 12), (1, 1, 1), (256, 50, 40), 3, "Float32"),     # degree 1, Nout 3, Float32
+    ((40, 23, 21), (5, 3, 3), (200, 70, 64), 1, "Float64"),      # degree 5 in dimension 1; tiles2 not a multiple of G2
+    ((16, 10, 40), (2, 3, 3), (128, 33, 17), 1, "Float64"),      # fewer samples than spans in dimension 3
+]
+
+
+@pytest.mark.parametrize("distribution", ["equispaced", "random"])
+@pytest.mark.parametrize("case", POST2_CASES, ids=[f"{c[0]}-{c[1]}-{c[4]}" for c in POST2_CASES])
+def test_double_march_post_kernel_vs_oracle(S, case, distribution, monkeypatch):
+    """Double march + fused post kernel (sg_adjoint_post2.cuh) against the C oracle; control points pre-filled with
+    garbage because this pipeline does its own zero fill; deterministic."""
+    from gpu_helpers import make_grid, oracle_adjoint
+    n_cp, deg, n_s, nout, ft = case
+    grid, cp, w, rng = make_grid(n_cp, deg, n_s, nout, ft, mdo=0, seed=41, distribution=distribution)
+    e = np.asfortranarray(rng.random(tuple(n_s) + (nout,)).astype(cp.dtype))
+    g = torch.full_like(grid.control_points.obtain(), -7.0)
+    monkeypatch.setenv("SG_ADJ_MARCH2", "1")
+    monkeypatch.setenv("SG_ADJ_MARCH3", "0")
+    S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g)
+    assert S.last_variant() == "adjoint_march2"
+    gref = oracle_adjoint(grid, e)
+    assert rel_err(S.to_numpy(g), gref) <= _tol(ft)
+    assert max_rel_err(S.to_numpy(g), gref) <= 10 * _tol(ft)
+    g2 = torch.full_like(g, 9.0)
+    S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g2)
+    if distribution == "equispaced":
+        assert torch.equal(g, g2)
+    # the separate combine + first-dimension kernels (SG_ADJ_M2_POST=0) give the same result
+    monkeypatch.setenv("SG_ADJ_M2_POST", "0")
+    g3 = torch.full_like(g, 1.0)
+    S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g3)
+    assert rel_err(S.to_numpy(g3), gref) <= _tol(ft)
+
+
 MARCH3_CASES = [
     # n_cp, degree, n_samples, nout, float type, extra environment
     ((20, 11, 9), (3, 3, 3), (128, 400, 20), 1, "Float64", {}),

@@ -8,10 +8,11 @@ import __graft_entry__ as entry  # noqa: E402
 
 n3 = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+slab = int(sys.argv[3]) if len(sys.argv) > 3 else 1          # > 1: the middle slab of a slab-sharded grid
 S = entry.load_package()
 S.set_synchronous(False)
 dims = tuple(S.SplineDimension(128, 3, n, float_type="Float64") for n in (512, 512, n3))
-grid = S.SplineGrid(dims, 1)
+grid = S.SlabShardedGrid(dims, 1, slab // 2, slab).local if slab > 1 else S.SplineGrid(dims, 1)
 e = S.jl_empty(grid.eval.shape, torch.float64, "cuda")
 e.copy_(torch.rand(e.shape, dtype=torch.float64, device="cuda"))
 g = torch.zeros_like(grid.control_points.obtain())
