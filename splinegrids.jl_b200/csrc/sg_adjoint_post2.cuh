@@ -50,18 +50,18 @@ __global__ void __launch_bounds__(128, 5) sg_adj_post2_kernel(T *__restrict__ cp
         }
         return;
     }
-    const int rows3 = G3 + P;
-    // the (<= 2, because G3 >= P) chunks of dimension 3 whose written rows contain i3
+    const int rows3 = G3 + P;                                           // row stride of a chunk in the partials (host worst case)
+    // the (<= 2, because G3e >= P) chunks of dimension 3 whose rows contain i3: chunk c holds the control indices
+    // [sf + c*G3e - P, min(sf + (c+1)*G3e, sl + 1) - 1]  (sg_m2_chunk_len)
     int64_t off0 = 0, off1 = 0;
     int nc = 0;
     {
-        const int64_t c_hi = min((i3 - 1) / G3, (int64_t)chunks3 - 1), c_lo = max((int64_t)0, (i3 - P - 1 + G3) / G3 - 1);
-        for (int64_t c = c_lo; c <= c_hi; ++c) {
-            const int64_t l3 = i3 - (c * G3 + 1);
-            if (l3 < 0 || l3 >= rows3) continue;
-            const int64_t cs_lo = max((int64_t)(P + 1 + c * G3), (int64_t)sf);
-            const int64_t cs_hi = min(min((int64_t)(P + 1 + c * G3 + G3), c3 + 1), (int64_t)sl + 1);
-            if (cs_lo >= cs_hi || i3 < cs_lo - P || i3 > cs_hi - 1) continue;   // rows this chunk really wrote
+        const int G3e = sg_m2_chunk_len(hdr, P, chunks3);
+        const int nch = (sl - sf + 1 + G3e - 1) / G3e;                 // chunks that hold samples
+        const int c_lo = i3 >= sf ? (int)((i3 - sf) / G3e) : 0;
+        const int c_hi = min((int)((i3 - sf + P) / G3e), nch - 1);
+        for (int c = c_lo; c <= c_hi; ++c) {
+            const int64_t l3 = i3 - ((int64_t)sf + (int64_t)c * G3e - P);
             // slot 0 of tile t in row l3 of chunk c
             const int64_t off = n1 * (int64_t)S * (t + (int64_t)tiles2 * (l3 + (int64_t)rows3 * (c + (int64_t)chunks3 * o)));
             if (nc == 0) off0 = off; else if (nc == 1) off1 = off;

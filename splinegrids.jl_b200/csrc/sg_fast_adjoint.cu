@@ -310,22 +310,22 @@ static SgMarch2Plan sg_adjoint_march2_plan(int nin, const int64_t *n_samples, co
     mp.G2 = SG_M2_G2;
     const int64_t nsp2 = n_cp[1] - P, nsp3 = n_cp[2] - P;
     mp.tiles2 = (int)((nsp2 + mp.G2 - 1) / mp.G2);
-    // enough threads: n1 * tiles2 * chunks3 * nout ~ 128K; chunks are cut over the spans that can hold samples
-    const int64_t base = n_samples[0] * mp.tiles2 * nout;
-    const int64_t chunks_needed = std::max<int64_t>(1, (294912 + base - 1) / base);   // ~300K threads (G3 ~ 7 on C3) measured best
-    const int64_t act_spans = std::min<int64_t>(nsp3, n_samples[2]);
-    int64_t G3 = std::max<int64_t>(std::max(2, P), act_spans / chunks_needed);   // G3 >= P: only neighbouring chunks overlap
+    // The number of chunks of dimension 3 is a CTA-count target (~2.9 waves of 3 CTAs x 148 SMs measured best on C3:
+    // long CTAs amortise the pipeline fill); the chunks adapt on device to the spans that hold samples
+    // (sg_m2_chunk_len), G3 is their worst-case length = the row stride of the partials.
+    const int64_t base = ((n_samples[0] + 127) / 128) * mp.tiles2 * nout;
+    int64_t chunks = std::max<int64_t>(1, (sg_env_int("SG_ADJ_M2_CTAS", 1280) + base / 2) / base);
     const int forced = sg_env_int("SG_ADJ_M2_G3", 0);
-    if (forced > 0) G3 = forced;
-    G3 = std::min<int64_t>(G3, nsp3);
+    if (forced > 0) chunks = (nsp3 + forced - 1) / forced;
+    chunks = std::min<int64_t>(chunks, std::max<int64_t>(1, nsp3 / std::max(2, P)));
+    const int64_t G3 = std::max<int64_t>(std::max(2, P), (nsp3 + chunks - 1) / chunks);   // G3 >= P: only neighbouring chunks overlap
     mp.G3 = (int)G3;
-    mp.chunks3 = (int)((nsp3 + G3 - 1) / G3);
+    mp.chunks3 = (int)chunks;
     if ((int64_t)mp.chunks3 * nout > 65535 || mp.tiles2 > 65535 || n_cp[1] > 65535 || n_cp[2] * nout > 65535) return mp;
     size_t off = 0;
     mp.part_off = off;
     off += sg_al256((size_t)n_samples[0] * (mp.G2 + P) * mp.tiles2 * (mp.G3 + P) * mp.chunks3 * nout * elem_size);
-    mp.r_off = off;
-    off += sg_al256((size_t)n_samples[0] * n_cp[1] * n_cp[2] * nout * elem_size);
+    mp.r_off = off;                                                     // (no intermediate array any more: the post kernel reads the partials)
     mp.bytes = off;
     mp.ok = true;
     return mp;
@@ -571,12 +571,6 @@ static int sg_launch_march2(const SgAdj2Args<T> &m, int nout, cudaStream_t st)
     return SG_OK;
 }
 
-// halo combine + dimension-1 contraction in one kernel (also zero-fills cp where nothing is written)
-static bool sg_m2_post_eligible(const SgMarch2Plan &mp, int P, int nout)
-{
-    return sg_env_int("SG_ADJ_M2_POST", 1) && mp.ok && mp.G3 >= P && SG_M2_G2 >= P && nout <= 65535;
-}
-
 template <typename T>
 static int sg_run_march2(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &ss, SgAdjointHeader *hdr, const T *eval,
                          const SgMarch2Plan &mp, char *ws, cudaStream_t st)
@@ -584,7 +578,6 @@ static int sg_run_march2(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &s
     const int P = a.degree[1];
     SgAdj2Args<T> m{};
     T *part = reinterpret_cast<T *>(ws + mp.part_off);
-    T *R = reinterpret_cast<T *>(ws + mp.r_off);
     m.X = eval; m.Y = part; m.table2 = a.table[1]; m.table3 = a.table[2]; m.index3 = a.index[2];
     m.start2 = ss.start[1]; m.start3 = ss.start[2]; m.hdr = hdr;
     m.n1 = a.n_samples[0]; m.n2 = a.n_samples[1]; m.n3 = a.n_samples[2]; m.c2 = a.n_cp[1]; m.c3 = a.n_cp[2];
@@ -596,7 +589,7 @@ static int sg_run_march2(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &s
         default: lrc = sg_launch_march2<T, 3>(m, a.nout, st); break;
     }
     if (lrc != SG_OK) return lrc;
-    if (sg_m2_post_eligible(mp, P, a.nout)) {
+    {
         // halo combine + contraction of dimension 1 in one kernel (sg_adjoint_post2.cuh): the partials are read once and
         // the (n1, c2, c3) intermediate never goes to HBM
         dim3 pgrid((unsigned)((mp.tiles2 + 1) * sg_blocks(a.n_cp[0], 128)), (unsigned)m.c3, (unsigned)a.nout);
@@ -608,46 +601,7 @@ static int sg_run_march2(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &s
         g_sg_launches.fetch_add(1);
         return SG_OK;
     }
-    if (sg_env_int("SG_ADJ_M2_SCAN", 1) && mp.G3 >= P && a.nout <= 65535) {
-        dim3 sgrid((unsigned)((m.n1 + 127) / 128), (unsigned)m.c3, (unsigned)a.nout);
-        switch (P) {
-            case 1: sg_adj_combine2_scan_kernel<T, 1, SG_M2_G2><<<sgrid, 128, 0, st>>>(R, part, hdr, m.n1, m.c2, m.c3, mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS); break;
-            case 2: sg_adj_combine2_scan_kernel<T, 2, SG_M2_G2><<<sgrid, 128, 0, st>>>(R, part, hdr, m.n1, m.c2, m.c3, mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS); break;
-            default: sg_adj_combine2_scan_kernel<T, 3, SG_M2_G2><<<sgrid, 128, 0, st>>>(R, part, hdr, m.n1, m.c2, m.c3, mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS); break;
-        }
-    } else {
-        dim3 cgrid((unsigned)((m.n1 + 127) / 128), (unsigned)((m.c2 + SG_COMBINE_ROWS - 1) / SG_COMBINE_ROWS), (unsigned)(m.c3 * a.nout));
-        sg_adj_combine2_kernel<T><<<cgrid, 128, 0, st>>>(R, part, hdr, m.n1, m.c2, m.c3, P, mp.G2, mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS);
-    }
-    g_sg_launches.fetch_add(1);
-    // pass B over dimension 1 on R (n1, c2, c3, nout); rows of the slowest axis outside the support are skipped
-    const int64_t outerB = a.cp_total / a.n_cp[0] * a.nout;
-    const int64_t avg_range = (int64_t)(a.degree[0] + 1) * a.n_samples[0] / a.n_cp[0];
-    const int b_last_dim = 2, b_last_P = a.degree[2];
-    const int64_t b_last_div = a.n_cp[1], b_last_c = a.n_cp[2];
-    if (avg_range <= 18) {
-        const int rpb = sg_env_int("SG_ADJ_RPB", 8);
-        dim3 rgrid(sg_blocks(a.n_cp[0], 128), (unsigned)((outerB + rpb - 1) / rpb));
-        if (rgrid.y > 65535) return SG_ERR_UNSUPPORTED;
-        sg_adj_first_dim_rows_kernel<T, 20, false><<<rgrid, 128, 0, st>>>(cp, R, a.table[0], a.index[0], ss.start[0], hdr, a.n_samples[0],
-                                                                         a.n_cp[0], outerB, a.degree[0], rpb, nullptr, a.cp_total,
-                                                                         SG_PATH_MULTIPASS, b_last_dim, b_last_P, b_last_div, b_last_c);
-    } else {
-        const unsigned gy = (unsigned)std::min<int64_t>(outerB, 32768);
-        if (avg_range >= 64) {
-            dim3 bgrid(sg_blocks(a.n_cp[0], 256 / 32), gy, (unsigned)((outerB + gy - 1) / gy));
-            sg_adj_first_dim_kernel<T, 32, false><<<bgrid, 256, 0, st>>>(cp, R, a.table[0], a.index[0], ss.start[0], hdr, a.n_samples[0], a.n_cp[0],
-                                                                        outerB, a.degree[0], nullptr, a.cp_total, SG_PATH_MULTIPASS, b_last_dim,
-                                                                        b_last_P, b_last_div, b_last_c);
-        } else {
-            dim3 bgrid(sg_blocks(a.n_cp[0], 256 / 8), gy, (unsigned)((outerB + gy - 1) / gy));
-            sg_adj_first_dim_kernel<T, 8, false><<<bgrid, 256, 0, st>>>(cp, R, a.table[0], a.index[0], ss.start[0], hdr, a.n_samples[0], a.n_cp[0],
-                                                                       outerB, a.degree[0], nullptr, a.cp_total, SG_PATH_MULTIPASS, b_last_dim,
-                                                                       b_last_P, b_last_div, b_last_c);
-        }
-    }
-    g_sg_launches.fetch_add(1);
-    return SG_OK;
+    return SG_ERR_UNSUPPORTED;   // not reached: the plan guarantees G3 >= P and G2 >= P
 }
 
 template <typename T>
@@ -665,7 +619,7 @@ int sg_evaluate_adjoint_fast(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T
     SgFusedPlan fp = sg_adjoint_fused_plan(a.nin, a.n_samples, a.n_cp, a.nout, a.degree, (int)sizeof(T), rational);
     if (fp.ok && reinterpret_cast<uintptr_t>(eval) % 16 != 0) fp.ok = false;
     const SgMarch2Plan mp = sg_adjoint_march2_plan(a.nin, a.n_samples, a.n_cp, a.nout, a.degree, (int)sizeof(T), rational);
-    const bool self_zero = m3.ok || (!fp.ok && sg_m2_post_eligible(mp, a.degree[1], a.nout));   // the last kernel writes every cp
+    const bool self_zero = m3.ok || (!fp.ok && mp.ok);   // the last kernel writes every cp
     if (!self_zero) SG_CUDA(cudaMemsetAsync(cp, 0, (size_t)a.cp_total * a.nout * sizeof(T), st));
     int rc;
     if (m3.ok) {

@@ -703,6 +703,16 @@ __global__ void __launch_bounds__(128) sg_adj_tile_combine_kernel(T *__restrict_
 // kernel).  For C3 the pass writes ~130 MB instead of the 268 + 67 MB of the two separate passes.
 // Rows of a span are processed RS at a time (any number of samples per span works).
 // =============================================================================================
+// Chunks of dimension 3 adapt to the spans that really hold samples (a slab of a sharded grid touches few of them):
+// the host fixes the NUMBER of chunks (a CTA-count target) and the worst-case chunk length a.G3 (row stride of the
+// partials); on device the active spans [span_first, span_last] are cut evenly, G3e = max(P, ceil(nact / chunks3)) <=
+// a.G3 spans per chunk, chunk c = spans [sf + c*G3e, sf + (c+1)*G3e).  G3e >= P: only neighbouring chunks overlap.
+__device__ __forceinline__ int sg_m2_chunk_len(const SgAdjointHeader *h, int P, int chunks3)
+{
+    const int nact = h->span_last[2] - h->span_first[2] + 1;
+    return max(max(P, 1), (nact + chunks3 - 1) / chunks3);
+}
+
 #define SG_M2_FAST_ROWS 5      // row slots per knot span in the TMA-fed kernel's straight-line contraction
 template <typename T>
 struct SgAdj2Args {
@@ -758,10 +768,9 @@ __device__ __forceinline__ void sg_adj_march2_body(const SgAdj2Args<T> &a, int o
         }
     }
     // spans of dimension 3 in this chunk, restricted to those that hold samples (slabs of a sharded grid)
-    const int s3_lo0 = P + 1 + c3k * a.G3;
-    const int s3_hi0 = (int)min((int64_t)s3_lo0 + a.G3, a.c3 + 1);
-    const int s3_lo = max(s3_lo0, a.hdr->span_first[2]);
-    const int s3_hi = min(s3_hi0, a.hdr->span_last[2] + 1);
+    const int G3e = sg_m2_chunk_len(a.hdr, P, a.chunks3);
+    const int s3_lo = a.hdr->span_first[2] + c3k * G3e;
+    const int s3_hi = min(s3_lo + G3e, a.hdr->span_last[2] + 1);
     if (s3_lo >= s3_hi) return;                                        // block-uniform
     const int64_t j3_lo = a.start3[s3_lo], j3_hi = a.start3[s3_hi];
     const int rows3 = a.G3 + P;
@@ -778,7 +787,7 @@ __device__ __forceinline__ void sg_adj_march2_body(const SgAdj2Args<T> &a, int o
     // Y index = j1 + n1*(slot + S*(tile2 + tiles2*(row3 + rows3*(chunk3 + chunks3*o))))
     const int64_t y_slot = a.n1;
     const int64_t y_row3 = a.n1 * (int64_t)S * a.tiles2;
-    T *__restrict__ yp = a.Y + j1 + a.n1 * ((int64_t)S * tile2) + y_row3 * ((int64_t)(s3_lo - s3_lo0) + (int64_t)rows3 * (c3k + (int64_t)a.chunks3 * o));
+    T *__restrict__ yp = a.Y + j1 + a.n1 * ((int64_t)S * tile2) + y_row3 * ((int64_t)rows3 * (c3k + (int64_t)a.chunks3 * o));
 
     auto emit_oldest = [&]() {
 #pragma unroll
@@ -884,42 +893,6 @@ __global__ void __launch_bounds__(128) sg_adj_march2_complement_kernel(const __g
         sg_adj_march2_body<T, P, G2, RS>(a, only_tiles_above_rows, (unsigned)(vb % nbx), (unsigned)((vb / nbx) % nby), (unsigned)(vb / ((uint64_t)nbx * nby)));
 }
 
-// R'[j1, i2, i3, o] = sum over tiles of dim 2 covering i2 and chunks of dim 3 covering i3 of the partials.
-// grid = (ceil(n1/128), ceil(c2/SG_COMBINE_ROWS), c3*nout)
-template <typename T>
-__global__ void __launch_bounds__(128) sg_adj_combine2_kernel(T *__restrict__ R, const T *__restrict__ Pp, const SgAdjointHeader *hdr,
-                                                              int64_t n1, int64_t c2, int64_t c3, int P, int G2, int tiles2, int G3,
-                                                              int chunks3, int path)
-{
-    if (!sg_adj_path_active(hdr, path)) return;
-    const int64_t j1 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j1 >= n1) return;
-    const int64_t i3 = (int64_t)(blockIdx.z % c3) + 1;                  // 1-based control indices
-    const int64_t o = blockIdx.z / c3;
-    const int sf = hdr->span_first[2], sl = hdr->span_last[2];
-    if (i3 < sf - P || i3 > sl) return;                                 // outside the support: never read downstream
-    const int S = G2 + P, rows3 = G3 + P;
-    const int64_t c_hi = min((i3 - 1) / G3, (int64_t)chunks3 - 1), c_lo = max((int64_t)0, (i3 - P - 1 + G3) / G3 - 1);
-    const int64_t i2_end = min((int64_t)(blockIdx.y + 1) * SG_COMBINE_ROWS, c2);
-    for (int64_t i2 = (int64_t)blockIdx.y * SG_COMBINE_ROWS + 1; i2 <= i2_end; ++i2) {
-        T acc = T(0);
-        const int64_t t_hi = min((i2 - 1) / G2, (int64_t)tiles2 - 1), t_lo = max((int64_t)0, (i2 - P - 1 + G2) / G2 - 1);
-        for (int64_t c = c_lo; c <= c_hi; ++c) {
-            const int64_t l3 = i3 - (c * G3 + 1);
-            if (l3 < 0 || l3 >= rows3) continue;
-            const int64_t cs_lo = max((int64_t)(P + 1 + c * G3), (int64_t)sf);
-            const int64_t cs_hi = min(min((int64_t)(P + 1 + c * G3 + G3), c3 + 1), (int64_t)sl + 1);
-            if (cs_lo >= cs_hi || i3 < cs_lo - P || i3 > cs_hi - 1) continue;   // rows this chunk really wrote
-            for (int64_t t = t_lo; t <= t_hi; ++t) {
-                const int64_t l2 = i2 - (t * G2 + 1);
-                if (l2 < 0 || l2 >= S) continue;
-                acc += __ldcs(Pp + j1 + n1 * (l2 + (int64_t)S * (t + (int64_t)tiles2 * (l3 + (int64_t)rows3 * (c + (int64_t)chunks3 * o)))));
-            }
-        }
-        R[j1 + n1 * ((i2 - 1) + c2 * ((i3 - 1) + c3 * o))] = acc;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // TMA-fed variant of the double march: the tile's rows of each sample plane (n_rows x 128 columns) are streamed
 // into an NS-stage shared-memory ring with 1-D bulk async copies (cp.async.bulk, one per row, issued by one
@@ -1002,10 +975,9 @@ __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_
         }
     }
 
-    const int s3_lo0 = P + 1 + c3k * a.G3;
-    const int s3_hi0 = (int)min((int64_t)s3_lo0 + a.G3, a.c3 + 1);
-    const int s3_lo = max(s3_lo0, a.hdr->span_first[2]);
-    const int s3_hi = min(s3_hi0, a.hdr->span_last[2] + 1);
+    const int G3e = sg_m2_chunk_len(a.hdr, P, a.chunks3);
+    const int s3_lo = a.hdr->span_first[2] + c3k * G3e;
+    const int s3_hi = min(s3_lo + G3e, a.hdr->span_last[2] + 1);
     if (s3_lo >= s3_hi) return;                                        // block-uniform
     const int64_t j3_lo = a.start3[s3_lo], j3_hi = a.start3[s3_hi];
     const int np_total = (int)(j3_hi - j3_lo);
@@ -1023,7 +995,7 @@ __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_
     // 32-bit element offsets into the partials (the host checks that they fit): fewer live registers in the plane loop
     const unsigned y_slot = (unsigned)a.n1;
     const unsigned y_row3 = (unsigned)(a.n1 * (int64_t)S * a.tiles2);
-    unsigned yoff = (unsigned)(j1 + a.n1 * ((int64_t)S * tile2) + (int64_t)y_row3 * ((int64_t)(s3_lo - s3_lo0) + (int64_t)rows3 * (c3k + (int64_t)a.chunks3 * o)));
+    unsigned yoff = (unsigned)(j1 + a.n1 * ((int64_t)S * tile2) + (int64_t)y_row3 * ((int64_t)rows3 * (c3k + (int64_t)a.chunks3 * o)));
     T *__restrict__ const ybase = a.Y;
     const unsigned row_bytes = (unsigned)(ncols * sizeof(T));
 
@@ -1113,63 +1085,4 @@ __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_
 #pragma unroll
         for (int s = 0; s < S; ++s) __stcs(ybase + (yoff + y_slot * s + y_row3 * k), acc3[s][k]);
     }
-}
-
-// Combine of the double-march partials as a sequential scan over the tiles of dimension 2 (needs G2 >= P, so only
-// neighbouring tiles overlap): a thread owns (j1, i3, o), walks the tiles t = 0..tiles2-1 and carries the P halo
-// slots from one tile to the next.  No integer divisions, all loads/stores coalesced along j1.
-// grid = (ceil(n1/128), c3, nout)
-template <typename T, int P, int G2>
-__global__ void __launch_bounds__(128) sg_adj_combine2_scan_kernel(T *__restrict__ R, const T *__restrict__ Pp, const SgAdjointHeader *hdr,
-                                                                   int64_t n1, int64_t c2, int64_t c3, int tiles2, int G3, int chunks3, int path)
-{
-    if (!sg_adj_path_active(hdr, path)) return;
-    constexpr int S = G2 + P;
-    const int64_t j1 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j1 >= n1) return;
-    const int64_t i3 = (int64_t)blockIdx.y + 1;                         // 1-based control index of dimension 3
-    const int64_t o = blockIdx.z;
-    const int sf = hdr->span_first[2], sl = hdr->span_last[2];
-    if (i3 < sf - P || i3 > sl) return;                                 // outside the support: never read downstream
-    const int rows3 = G3 + P;
-    // the (<= 2 when G3 >= P) chunks of dimension 3 whose written rows contain i3
-    int64_t cc[4], ll[4];
-    int nc = 0;
-    const int64_t c_hi = min((i3 - 1) / G3, (int64_t)chunks3 - 1), c_lo = max((int64_t)0, (i3 - P - 1 + G3) / G3 - 1);
-    for (int64_t c = c_lo; c <= c_hi && nc < 4; ++c) {
-        const int64_t l3 = i3 - (c * G3 + 1);
-        if (l3 < 0 || l3 >= rows3) continue;
-        const int64_t cs_lo = max((int64_t)(P + 1 + c * G3), (int64_t)sf);
-        const int64_t cs_hi = min(min((int64_t)(P + 1 + c * G3 + G3), c3 + 1), (int64_t)sl + 1);
-        if (cs_lo >= cs_hi || i3 < cs_lo - P || i3 > cs_hi - 1) continue;
-        cc[nc] = c; ll[nc] = l3; ++nc;
-    }
-    T carry[P];
-#pragma unroll
-    for (int k = 0; k < P; ++k) carry[k] = T(0);
-    T *__restrict__ out = R + j1 + n1 * (c2 * ((i3 - 1) + c3 * o));
-    const int64_t t_stride = n1 * (int64_t)S;                           // between tiles
-    for (int t = 0; t < tiles2; ++t) {
-        T v[S];
-#pragma unroll
-        for (int q = 0; q < S; ++q) v[q] = T(0);
-        for (int e = 0; e < nc; ++e) {
-            const T *__restrict__ src = Pp + j1 + t_stride * (t + (int64_t)tiles2 * (ll[e] + (int64_t)rows3 * (cc[e] + (int64_t)chunks3 * o)));
-#pragma unroll
-            for (int q = 0; q < S; ++q) v[q] += __ldcs(src + n1 * q);
-        }
-#pragma unroll
-        for (int k = 0; k < P; ++k) v[k] += carry[k];
-        const int64_t i2_0 = (int64_t)t * G2;                           // 0-based control index of slot 0
-#pragma unroll
-        for (int q = 0; q < G2; ++q)
-            if (i2_0 + q < c2) out[n1 * (i2_0 + q)] = v[q];
-#pragma unroll
-        for (int k = 0; k < P; ++k) carry[k] = v[G2 + k];
-    }
-    // the last tile's halo slots are real control indices (c2 = nspans + P)
-    const int64_t i2_0 = (int64_t)tiles2 * G2;
-#pragma unroll
-    for (int k = 0; k < P; ++k)
-        if (i2_0 + k < c2) out[n1 * (i2_0 + k)] = carry[k];
 }

@@ -260,11 +260,12 @@ def test_double_march_post_kernel_vs_oracle(S, case, distribution, monkeypatch):
     S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g2)
     if distribution == "equispaced":
         assert torch.equal(g, g2)
-    # the separate combine + first-dimension kernels (SG_ADJ_M2_POST=0) give the same result
-    monkeypatch.setenv("SG_ADJ_M2_POST", "0")
-    g3 = torch.full_like(g, 1.0)
-    S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g3)
-    assert rel_err(S.to_numpy(g3), gref) <= _tol(ft)
+    # other chunkings of dimension 3 (CTA-count target) give the same result up to summation order
+    for ctas in ("1", "100000"):
+        monkeypatch.setenv("SG_ADJ_M2_CTAS", ctas)
+        g3 = torch.full_like(g, 1.0)
+        S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g3)
+        assert rel_err(S.to_numpy(g3), gref) <= _tol(ft), ctas
 
 
 MARCH3_CASES = [
