@@ -15,6 +15,7 @@ from .control_points import (DefaultControlPoints, LocallyRefinedControlPoints, 
                              activate_local_control_point_range_, activate_local_refinement_, copyto_,
                              deactivate_overwritten_control_points_, get_n_control_points, obtain)
 from .distributed import PeerGradientExchange, SlabShardedGrid, allreduce_gradient_, slab_bounds
+from .graphs import CapturedCalls
 from .knot_vector import KnotVector
 from .linear_map import SplineGridLinearMap
 from .refinement import (add_default_local_refinement, boehm_refinement_matrix, error_informed_local_refinement_,
@@ -33,5 +34,5 @@ __all__ = [
     "copyto_", "SplineGridLinearMap", "SlabShardedGrid", "PeerGradientExchange", "allreduce_gradient_", "slab_bounds", "to_device", "to_numpy",
     "jl_zeros", "jl_ones", "jl_empty", "reshape_colmajor", "is_colmajor", "as_colmajor", "set_synchronous",
     "is_synchronous", "asynchronous", "set_kernel_policy", "last_variant", "launch_count", "launch_count_reset",
-    "SplineGridsError", "SplineGridsB200Error", "boehm_refinement_matrix",
+    "SplineGridsError", "SplineGridsB200Error", "boehm_refinement_matrix", "CapturedCalls",
 ]
