@@ -242,7 +242,9 @@ def main_gpu(args):
     # The step is captured once in a CUDA graph (two steps per replay: the peer-memory exchange alternates between two
     # staging buffers) and replayed: the same kernels, without the per-call host cost that bounds thin slabs.
     cap, cap_err = None, None
-    if not args.no_graph:
+    # N > 1: eager by default -- capturing the symmetric-memory barrier / NCCL all-reduce in a graph hung (barrier) or
+    # blocked the process-group teardown (NCCL) when tried at N = 2; `--graph` forces the attempt.
+    if (world == 1 and not args.no_graph) or args.graph:
         try:
             cap = S.CapturedCalls(step, unroll=2, warmup=1)
             for _ in range(2):
@@ -414,6 +416,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nccl-allreduce", action="store_true", help="N>1: use the NCCL all-reduce instead of the peer-memory exchange")
+    ap.add_argument("--graph", action="store_true", help="N>1: also try to capture the step (with its gradient exchange) in a CUDA graph")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--check", action="store_true", help="N>1: verify the exchanged gradient against an NCCL all-reduce")
     ap.add_argument("--traffic-bytes", type=float, default=None,

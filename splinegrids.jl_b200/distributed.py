@@ -98,24 +98,33 @@ class PeerGradientExchange:
         self._k0s = _lib.i64_array(self.k0)
         self._nps = _lib.i64_array(self.np_)
         self.step = 0
+        self._prepared = {}
 
     def exchange_(self, grad: torch.Tensor) -> torch.Tensor:
         from . import _lib
         C = _lib.C
         b = self.step & 1
         self.step += 1
-        suf = _lib.suffix(self.dtype)
         st = _lib.stream_ptr(self.device)
-        lib = _lib.lib()
-        _lib.check(getattr(lib, "sg_exchange_push_" + suf)(
-            _lib.ptr(grad), self.peer_ptrs[b], C.c_int(self.world), C.c_int(self.rank), C.c_int64(self.plane_elems),
-            C.c_int64(self.c_last), C.c_int(self.nout), C.c_int64(self.k0[self.rank]), C.c_int64(self.np_[self.rank]),
-            C.c_int64(self.max_planes), st), "sg_exchange_push")
+        key = (b, grad.data_ptr())
+        prep = self._prepared.get(key)
+        if prep is None:                                    # marshal once per (staging buffer, gradient array)
+            suf = _lib.suffix(self.dtype)
+            lib = _lib.lib()
+            prep = (getattr(lib, "sg_exchange_push_" + suf),
+                    (_lib.ptr(grad), self.peer_ptrs[b], C.c_int(self.world), C.c_int(self.rank), C.c_int64(self.plane_elems),
+                     C.c_int64(self.c_last), C.c_int(self.nout), C.c_int64(self.k0[self.rank]), C.c_int64(self.np_[self.rank]),
+                     C.c_int64(self.max_planes)),
+                    getattr(lib, "sg_exchange_reduce_" + suf),
+                    (_lib.ptr(grad), _lib.ptr(self.stage[b]), C.c_int(self.world), self._k0s, self._nps,
+                     C.c_int64(self.plane_elems), C.c_int64(self.c_last), C.c_int(self.nout), C.c_int64(self.max_planes)))
+            if len(self._prepared) >= 16:
+                self._prepared.clear()
+            self._prepared[key] = prep
+        push, push_args, reduce_, reduce_args = prep
+        _lib.check(push(*push_args, st), "sg_exchange_push")
         self.hdl[b].barrier(channel=0)                      # stream-ordered, all ranks
-        _lib.check(getattr(lib, "sg_exchange_reduce_" + suf)(
-            _lib.ptr(grad), _lib.ptr(self.stage[b]), C.c_int(self.world), self._k0s, self._nps,
-            C.c_int64(self.plane_elems), C.c_int64(self.c_last), C.c_int(self.nout), C.c_int64(self.max_planes), st),
-            "sg_exchange_reduce")
+        _lib.check(reduce_(*reduce_args, st), "sg_exchange_reduce")
         return grad
 
 

@@ -129,6 +129,27 @@ def _check_arrays(grid: SplineGrid, control_points, eval_):
     return cp
 
 
+# Prepared calls: a fitting loop calls evaluate! / evaluate_adjoint! thousands of times with the same arrays, and on
+# a thin slab of a sharded grid the kernels take only tens of microseconds, so the host side of a repeated call must
+# be a dictionary look-up plus one foreign call.  The key holds everything the marshalled arguments depend on (array
+# addresses, shapes are implied by the validated first call); a new array, derivative order or rebuilt table misses.
+_PREPARED_MAX = 64
+
+
+def _prepared_key(kind, grid, der, cp, eval_):
+    return (kind, der, cp.data_ptr(), eval_.data_ptr(), cp.shape, cp.stride(), cp.dtype, eval_.shape, eval_.stride(),
+            eval_.dtype, 0 if grid.weights is None else grid.weights.data_ptr(),
+            tuple(sd.eval.data_ptr() for sd in grid.spline_dimensions),
+            tuple(sd.sample_indices.data_ptr() for sd in grid.spline_dimensions))
+
+
+def _prepared_store(grid, key, value):
+    cache = grid.__dict__.setdefault("_prepared", {})
+    if len(cache) >= _PREPARED_MAX:
+        cache.clear()
+    cache[key] = value
+
+
 def evaluate_(obj, *, derivative_order: Optional[Sequence[int]] = None, control_points=None, eval=None) -> None:
     """``evaluate!`` -- dispatches like the reference's methods:
 
@@ -144,15 +165,25 @@ def evaluate_(obj, *, derivative_order: Optional[Sequence[int]] = None, control_
     grid: SplineGrid = obj
     nin = grid.Nin
     der = tuple(int(d) for d in derivative_order) if derivative_order is not None else (0,) * nin
-    assert len(der) == nin
-    validate_partial_derivatives(grid.spline_dimensions, der, is_nurbs=grid.is_nurbs())
     control_points = grid.control_points if control_points is None else control_points
     eval_ = grid.eval if eval is None else eval
-    cp = _check_arrays(grid, control_points, eval_)
-    with torch.cuda.device(grid.device):
+    cp = obtain(control_points)
+    key = _prepared_key("fwd", grid, der, cp, eval_)
+    prep = grid.__dict__.get("_prepared", {}).get(key)
+    if prep is None:
+        assert len(der) == nin
+        validate_partial_derivatives(grid.spline_dimensions, der, is_nurbs=grid.is_nurbs())
+        cp = _check_arrays(grid, control_points, eval_)
         fn = getattr(_lib.lib(), "sg_evaluate_" + _lib.suffix(grid.dtype))
-        _lib.check(fn(_lib.ptr(eval_), *_grid_call_args(grid, der), _lib.ptr(cp), _lib.ptr(grid.weights),
-                      _lib.stream_ptr(grid.device)), "sg_evaluate")
+        # the tuple keeps the marshalled ctypes arrays (and through them nothing else) alive
+        prep = (fn, (_lib.ptr(eval_), *_grid_call_args(grid, der), _lib.ptr(cp), _lib.ptr(grid.weights)), grid.device.index)
+        _prepared_store(grid, key, prep)
+    fn, args, dev_index = prep
+    if torch.cuda.current_device() == dev_index:
+        _lib.check(fn(*args, _lib.stream_ptr(grid.device)), "sg_evaluate")
+    else:
+        with torch.cuda.device(grid.device):
+            _lib.check(fn(*args, _lib.stream_ptr(grid.device)), "sg_evaluate")
     after_launch(grid.device)
     return None
 
@@ -177,7 +208,7 @@ def _workspace(grid: SplineGrid) -> torch.Tensor:
 
 
 def evaluate_adjoint_(obj, *, derivative_order: Optional[Sequence[int]] = None, control_points=None,
-                      eval=None, allow_nurbs: bool = False) -> None:
+                      eval=None, allow_nurbs: bool = False, _retry: bool = False) -> None:
     """``evaluate_adjoint!`` -- src/adjoint.jl:52-83 (K4) for a grid; src/adjoint.jl:172-205 for control
     points.  Overwrites ``control_points`` (zero fill first, :61) with the adjoint applied to ``eval``.
 
@@ -191,14 +222,29 @@ def evaluate_adjoint_(obj, *, derivative_order: Optional[Sequence[int]] = None, 
                         "Adjoint evaluation not supported for NURBS.")
     nin = grid.Nin
     der = tuple(int(d) for d in derivative_order) if derivative_order is not None else (0,) * nin
-    validate_partial_derivatives(grid.spline_dimensions, der, is_nurbs=grid.is_nurbs())
     control_points = grid.control_points if control_points is None else control_points
     eval_ = grid.eval if eval is None else eval
-    cp = _check_arrays(grid, control_points, eval_)
-    ws = _workspace(grid)
-    with torch.cuda.device(grid.device):
+    cp = obtain(control_points)
+    key = _prepared_key("adj", grid, der, cp, eval_)
+    prep = grid.__dict__.get("_prepared", {}).get(key)
+    if prep is None:
+        validate_partial_derivatives(grid.spline_dimensions, der, is_nurbs=grid.is_nurbs())
+        cp = _check_arrays(grid, control_points, eval_)
+        ws = _workspace(grid)
         fn = getattr(_lib.lib(), "sg_evaluate_adjoint_" + _lib.suffix(grid.dtype))
-        _lib.check(fn(_lib.ptr(cp), *_grid_call_args(grid, der), _lib.ptr(eval_), _lib.ptr(grid.weights),
-                      _lib.ptr(ws), C.c_size_t(ws.numel()), _lib.stream_ptr(grid.device)), "sg_evaluate_adjoint")
+        prep = (fn, (_lib.ptr(cp), *_grid_call_args(grid, der), _lib.ptr(eval_), _lib.ptr(grid.weights), _lib.ptr(ws),
+                     C.c_size_t(ws.numel())), grid.device.index, ws)
+        _prepared_store(grid, key, prep)
+    fn, args, dev_index = prep[0], prep[1], prep[2]
+    if torch.cuda.current_device() == dev_index:
+        status = fn(*args, _lib.stream_ptr(grid.device))
+    else:
+        with torch.cuda.device(grid.device):
+            status = fn(*args, _lib.stream_ptr(grid.device))
+    if status == -3 and not _retry:            # SG_ERR_WORKSPACE: the pipeline choice (tuning environment) changed since
+        grid.__dict__.get("_prepared", {}).pop(key, None)   # the call was prepared -> size the workspace again
+        return evaluate_adjoint_(obj, derivative_order=derivative_order, control_points=control_points, eval=eval,
+                                 allow_nurbs=allow_nurbs, _retry=True)
+    _lib.check(status, "sg_evaluate_adjoint")
     after_launch(grid.device)
     return None
