@@ -3,6 +3,7 @@
 // prep kernel, no host synchronisation): with monotone spans the samples whose window contains
 // control index i form one contiguous range per dimension.
 #pragma once
+#include <climits>
 #include "sg_common.cuh"
 
 // span_start[d][s] (s = 0..n_cp+1, 1-based span s) = first sample j with index[j] >= s
@@ -16,12 +17,55 @@ struct SgSpanStarts {
     int32_t *tile_ni;
     int tile_size;
     int n_tiles;
+    // gather table of dimension 1 (used by the double march's post kernel): for every control index i the first sample
+    // of its support, the number of samples, and the first SG_GATHER_RMAX basis weights B1[lo + r, i - span + p]
+    int32_t *g_lo;     // [c_1][2] = (lo, len)
+    T *g_w;            // [SG_GATHER_RMAX][c_1]
 };
+#define SG_GATHER_RMAX 20
 
 template <typename T>
 __global__ void sg_adjoint_prep_kernel(const __grid_constant__ SgGridArgs<T> a, const __grid_constant__ SgSpanStarts<T> ss,
                                        SgAdjointHeader *hdr)
 {
+    if ((int)blockIdx.y == a.nin) {
+        // extra row of blocks: the gather table of dimension 1 (binary searches of its own: no dependence on start[])
+        if (ss.g_lo == nullptr) return;
+        const int64_t n0 = a.n_samples[0], c0 = a.n_cp[0];
+        const int p0 = a.degree[0];
+        const int32_t *__restrict__ idx0 = a.index[0];
+        for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < c0; i0 += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t i = i0 + 1;
+            const int64_t s0 = i > p0 + 1 ? i : p0 + 1, s1 = (i + p0 < c0 ? i + p0 : c0) + 1;
+            int64_t lo = 0, hi = n0;
+            while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (idx0[mid] >= s0) hi = mid; else lo = mid + 1; }
+            const int64_t first = lo;
+            // the spans of the next SG_GATHER_RMAX samples (independent loads) give the weights' columns and, for
+            // monotone spans, the length of the support; only longer supports need the second binary search
+            int sp[SG_GATHER_RMAX];
+#pragma unroll
+            for (int r = 0; r < SG_GATHER_RMAX; ++r) sp[r] = first + r < n0 ? idx0[first + r] : INT_MAX;
+            int len = 0;
+#pragma unroll
+            for (int r = 0; r < SG_GATHER_RMAX; ++r) len += sp[r] < s1 ? 1 : 0;
+            if (len == SG_GATHER_RMAX) {
+                hi = n0;
+                while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (idx0[mid] >= s1) hi = mid; else lo = mid + 1; }
+                len = (int)(lo - first);
+            }
+            ss.g_lo[2 * i0] = (int32_t)first;
+            ss.g_lo[2 * i0 + 1] = len;
+            T w[SG_GATHER_RMAX];
+#pragma unroll
+            for (int r = 0; r < SG_GATHER_RMAX; ++r) {
+                const int k = min(max((int)(i - sp[r] + p0), 0), p0);       // clamp: garbage-safe for non-monotone spans
+                w[r] = r < len ? a.table[0][first + r + n0 * k] : T(0);
+            }
+#pragma unroll
+            for (int r = 0; r < SG_GATHER_RMAX; ++r) ss.g_w[(int64_t)r * c0 + i0] = w[r];
+        }
+        return;
+    }
     const int d = blockIdx.y;
     const int64_t n = a.n_samples[d];
     const int32_t *__restrict__ idx = a.index[d];

@@ -23,8 +23,8 @@
 // grid = ((tiles2 + 1) * ceil(c1 / 128), c3, nout); requires G2 >= P (only neighbouring tiles overlap)
 template <typename T, int P, int G2>
 __global__ void __launch_bounds__(128, 5) sg_adj_post2_kernel(T *__restrict__ cp, const T *__restrict__ Pp, const T *__restrict__ table1,
-                                                           const int32_t *__restrict__ index1, const int32_t *__restrict__ start1,
-                                                           const SgAdjointHeader *hdr, int64_t n1, int64_t c1, int64_t c2, int64_t c3, int P1,
+                                                           const int32_t *__restrict__ index1, const int32_t *__restrict__ g_lo,
+                                                           const T *__restrict__ g_w, const SgAdjointHeader *hdr, int64_t n1, int64_t c1, int64_t c2, int64_t c3, int P1,
                                                            int tiles2, int G3, int chunks3, int path)
 {
     constexpr int S = G2 + P;
@@ -37,6 +37,20 @@ __global__ void __launch_bounds__(128, 5) sg_adj_post2_kernel(T *__restrict__ cp
     const int64_t o = blockIdx.z;
     const int64_t i2_0 = (int64_t)t * G2;                               // 0-based control row of slot 0
     if (i2_0 >= c2) return;
+    // Round 1 of loads, all independent of each other and of the header: this thread's entry of the gather table of
+    // dimension 1 (prep kernel) -- first sample, number of samples, basis weights -- and the block's sample range.
+    constexpr int RMAX = SG_POST2_RMAX;
+    static_assert(SG_POST2_RMAX == SG_GATHER_RMAX, "gather table width");
+    const int64_t i1 = ib * 128 + tid;                                   // 0-based control index of dimension 1
+    const bool valid = i1 < c1;
+    const int64_t i1c = valid ? i1 : c1 - 1;
+    const int2 gl = *reinterpret_cast<const int2 *>(g_lo + 2 * i1c);
+    const int lo_first = sg_ldg(g_lo + 2 * (ib * 128));
+    const int64_t i_last = min(ib * 128 + 127, c1 - 1);
+    const int2 gz = *reinterpret_cast<const int2 *>(g_lo + 2 * i_last);
+    T w[RMAX];
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r) w[r] = sg_ldg(g_w + (int64_t)r * c1 + i1c);
     const int sf = hdr->span_first[2], sl = hdr->span_last[2];
     // This kernel writes EVERY control point (no memset before the pipeline): zeros outside the support of this (slab
     // of the) grid, and zeros everywhere if the prep kernel flagged non-monotone spans (the scatter kernel accumulates).
@@ -71,36 +85,14 @@ __global__ void __launch_bounds__(128, 5) sg_adj_post2_kernel(T *__restrict__ cp
     }
     const bool own = t < tiles2, prev = t >= 1;                          // CTA-uniform sources
 
-    // this thread's control index and its sample range; the block's sample range
-    const int64_t i1 = ib * 128 + tid;                                   // 0-based
-    const bool valid = i1 < c1;
-    int64_t lo = 0, hi = 0;
-    if (valid) {
-        const int64_t i = i1 + 1;
-        const int64_t s0 = i > P1 + 1 ? i : P1 + 1;
-        const int64_t s1 = i + P1 < c1 ? i + P1 : c1;
-        lo = start1[s0]; hi = start1[s1 + 1];
-    }
-    int64_t jb_lo, jb_hi;
-    {
-        const int64_t ia = ib * 128 + 1, iz = min(ib * 128 + 128, c1);
-        jb_lo = start1[ia > P1 + 1 ? ia : P1 + 1];
-        jb_hi = start1[(iz + P1 < c1 ? iz + P1 : c1) + 1];
-    }
-    // Gather weights of this control index in registers (they do not depend on the row): two rounds of independent
-    // loads (span indices, then table entries) instead of a dependent chain per sample.  Ranges longer than RMAX, or a
-    // block range longer than one piece, take the look-up loop below.
-    constexpr int RMAX = SG_POST2_RMAX;
-    const int len_i = (int)(hi - lo);
-    const bool regw = __syncthreads_and((!valid || len_i <= RMAX) ? 1 : 0) && (jb_hi - jb_lo) <= JMAX;   // CTA-uniform
-    T w[RMAX];
-    if (regw) {
-        int kk[RMAX];
-#pragma unroll
-        for (int r = 0; r < RMAX; ++r) kk[r] = r < len_i ? (int)(i1 + 1 - sg_ldg(index1 + lo + r) + P1) : 0;
-#pragma unroll
-        for (int r = 0; r < RMAX; ++r) w[r] = r < len_i ? sg_ldg(table1 + lo + r + n1 * kk[r]) : T(0);
-    }
+    // this thread's sample range [lo, hi) and the block's [jb_lo, jb_hi) (spans are monotone: the last control index
+    // of the block ends last)
+    const int64_t lo = gl.x, hi = (int64_t)gl.x + gl.y;
+    const int len_i = valid ? gl.y : 0;
+    const int64_t jb_lo = lo_first, jb_hi = (int64_t)gz.x + gz.y;
+    // weights in registers (loaded above); ranges longer than RMAX, or a block range longer than one piece, take the
+    // look-up loop below
+    const bool regw = __syncthreads_and(len_i <= RMAX ? 1 : 0) && (jb_hi - jb_lo) <= JMAX;   // CTA-uniform
     T acc[G2];
 #pragma unroll
     for (int q = 0; q < G2; ++q) acc[q] = T(0);

@@ -43,6 +43,7 @@ struct SgAdjointLayout {
     size_t header;               // offset 0
     size_t starts[SG_MAX_DIMS];  // int32[n_cp+2] per dimension
     size_t tile_lo, tile_ni;     // int32[n_tiles] each (fused adjoint)
+    size_t g_lo, g_w;            // gather table of dimension 1: int32[c_1][2], T[SG_GATHER_RMAX][c_1]
     int n_tiles, tile_size;
     size_t denom;                // T[n_total] (rational only), else 0
     size_t fast;                 // scratch of the tiled fast path
@@ -66,6 +67,10 @@ static SgAdjointLayout sg_adjoint_layout(int nin, const int64_t *n_samples, cons
     off += sg_align256((size_t)L.n_tiles * sizeof(int32_t));
     L.tile_ni = off;
     off += sg_align256((size_t)L.n_tiles * sizeof(int32_t));
+    L.g_lo = off;
+    off += sg_align256((size_t)n_cp[0] * 2 * sizeof(int32_t));
+    L.g_w = off;
+    off += sg_align256((size_t)n_cp[0] * SG_GATHER_RMAX * elem_size);
     L.denom = off;
     if (rational) off += sg_align256((size_t)n_total * elem_size);
     L.fast = off;
@@ -129,12 +134,14 @@ static int sg_evaluate_adjoint_impl(T *cp, int nin, const int64_t *n_samples, co
     ss.tile_ni = reinterpret_cast<int32_t *>(ws + L.tile_ni);
     ss.tile_size = L.tile_size;
     ss.n_tiles = L.n_tiles;
+    ss.g_lo = reinterpret_cast<int32_t *>(ws + L.g_lo);
+    ss.g_w = reinterpret_cast<T *>(ws + L.g_w);
     max_len = std::max<int64_t>(max_len, L.n_tiles);
     rc = SG_OK;
     do {
         cudaError_t e = cudaMemsetAsync(hdr, 0, sizeof(SgAdjointHeader), st);
         if (e != cudaSuccess) { rc = (int)e; break; }
-        dim3 pgrid((unsigned)std::min<int64_t>((max_len + 255) / 256, 64), nin);
+        dim3 pgrid((unsigned)std::min<int64_t>((max_len + 255) / 256, 64), nin + 1);   // + 1: gather table of dimension 1
         sg_adjoint_prep_kernel<T><<<pgrid, 256, 0, st>>>(a, ss, hdr);
         g_sg_launches.fetch_add(1);
 
