@@ -315,17 +315,55 @@ def main_gpu(args):
                              "frac_of_hbm_roofline": nb_local / (ms_adj * 1e-3) / 1e9 / hbm,
                              "note": "local kernels only (no all-reduce)"},
     }
+    # dominant kernel of the step (49 % of it, profiles/r01_ncu_launch_shares.txt): the TMA-fed double march of the
+    # adjoint.  Its launch duration is measured live with CUDA events recorded by the library on the launch stream
+    # right before / after the kernel (sg_profile_adjoint_main, include/splinegrids_b200.h).
+    ms_main = None
+    if var_adj == "adjoint_march2":
+        lib = S._lib.lib()
+        lib.sg_profile_adjoint_main(1)
+        samples = []
+        for _ in range(reps):
+            S.evaluate_adjoint_(grid, eval=e_in, control_points=grad)
+            t = float(lib.sg_profile_adjoint_main_ms())
+            if t > 0:
+                samples.append(t)
+        lib.sg_profile_adjoint_main(0)
+        if samples:
+            ms_main = float(np.mean(samples))
     # roofline kernel = the forward march kernel (ONE launch == the whole evaluate! call, so its CUDA-event time is
     # the kernel's launch duration).  The adjoint is a chain of kernels; its op-level fraction is in "also"/"ops".
-    roofline = {"kernel": f"sg_eval3d_march_kernel<double,3,2,4,4,TMA={'true' if var_fwd.endswith('tma') else 'false'}> "
+    fwd_roof = {"kernel": f"sg_eval3d_march_kernel<double,3,2,4,4,TMA={'true' if var_fwd.endswith('tma') else 'false'}> "
                           f"[{var_fwd}] (evaluate!, one launch per call)",
                 "share_of_step": ms_fwd / (ms_fwd + ms_adj),
                 "bound": "hbm", "achieved": ops["evaluate"]["achieved_GBs"], "peak": hbm, "unit": "GB/s",
                 "frac": ops["evaluate"]["frac_of_hbm_roofline"], "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                 "algorithmic_bytes_per_launch": nb_local, "traffic": args.traffic_bytes,
                 "traffic_source": "profiles/r01_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, "
-                                  "N=1 full grid)" if args.traffic_bytes else None,
-                "also": {"evaluate_adjoint_op_frac": ops["evaluate_adjoint"]["frac_of_hbm_roofline"]}}
+                                  "N=1 full grid)" if args.traffic_bytes else None}
+    if ms_main is not None:
+        # algorithmic bytes of this launch: the sample array read once + the tables/indices (SURVEY 8d's adjoint
+        # figure minus the control-point write, which the post kernel does)
+        nb_main = nb_local - int(np.prod(w["n_cp"])) * w["nout"] * 8
+        tr_main = None
+        tp = ROOT / "profiles" / "r01_traffic.json"
+        if tp.exists() and world == 1:
+            k = json.loads(tp.read_text()).get("adjoint", {}).get("sg_adj_march2_tma_kernel")
+            if k:
+                tr_main = float(k["read"] + k["write"])
+        roofline = {"kernel": "sg_adj_march2_tma_kernel<double,3,4,20,3> (evaluate_adjoint!: TMA-fed double march over the sample "
+                              "array; dominant kernel of the step)",
+                    "share_of_step": ms_main / (ms_fwd + ms_adj), "bound": "hbm",
+                    "achieved": nb_main / (ms_main * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                    "frac": nb_main / (ms_main * 1e-3) / 1e9 / hbm, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+                    "launch_ms": ms_main, "algorithmic_bytes_per_launch": nb_main, "traffic": tr_main,
+                    "traffic_source": "profiles/r01_traffic.json (ncu --set full, N=1 full grid; includes the 135 MB of tile/chunk "
+                                      "partials the kernel writes)" if tr_main else None,
+                    "timing": "CUDA events recorded by the library on the launch stream around this kernel",
+                    "also": {"evaluate_adjoint_op_frac": ops["evaluate_adjoint"]["frac_of_hbm_roofline"],
+                             "evaluate_kernel": fwd_roof}}
+    else:
+        roofline = dict(fwd_roof, also={"evaluate_adjoint_op_frac": ops["evaluate_adjoint"]["frac_of_hbm_roofline"]})
 
     # ---- end-to-end through the public API with HOST buffers -------------------------------------
     e2e_steps = max(1, min(args.steps, args.e2e_steps))

@@ -55,6 +55,11 @@ void sg_launch_count_reset(void);
 void sg_set_kernel_policy(int policy);
 /* Name of the kernel variant chosen by the last sg_evaluate / sg_evaluate_adjoint call. */
 const char *sg_last_variant(void);
+/* Benchmark hook: when enabled, sg_evaluate_adjoint records a CUDA event on the caller's stream right before and right
+ * after its dominant kernel (the TMA-fed double march over the sample array); sg_profile_adjoint_main_ms waits for
+ * the second event and returns the kernel's duration in milliseconds (< 0: nothing recorded).  Process-wide. */
+void sg_profile_adjoint_main(int enable);
+float sg_profile_adjoint_main_ms(void);
 
 /* ---- K9 expand_knot_vector_kernel -- src/util_kernels.jl:1-20, launcher src/knot_vector.jl:29-37
  * knots_all[sum(mult)] <- knot_values[i] repeated multiplicities[i] times. */

@@ -545,6 +545,31 @@ static int sg_run_fused(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &ss
     return SG_OK;
 }
 
+// benchmark hook (include/splinegrids_b200.h): CUDA events around the dominant kernel
+static int g_sg_prof_on = 0, g_sg_prof_recorded = 0;
+static cudaEvent_t g_sg_prof_ev[2] = {nullptr, nullptr};
+extern "C" void sg_profile_adjoint_main(int enable)
+{
+    g_sg_prof_on = enable != 0;
+    g_sg_prof_recorded = 0;
+    if (g_sg_prof_on && !g_sg_prof_ev[0]) {
+        if (cudaEventCreate(&g_sg_prof_ev[0]) != cudaSuccess || cudaEventCreate(&g_sg_prof_ev[1]) != cudaSuccess) {
+            cudaGetLastError();
+            g_sg_prof_on = 0;
+        }
+    }
+}
+extern "C" float sg_profile_adjoint_main_ms(void)
+{
+    if (!g_sg_prof_recorded) return -1.0f;
+    float ms = -1.0f;
+    if (cudaEventSynchronize(g_sg_prof_ev[1]) != cudaSuccess || cudaEventElapsedTime(&ms, g_sg_prof_ev[0], g_sg_prof_ev[1]) != cudaSuccess) {
+        cudaGetLastError();
+        return -1.0f;
+    }
+    return ms;
+}
+
 #define SG_M2_RTMAX 20
 #define SG_M2_NS 3
 template <typename T, int P>
@@ -560,7 +585,9 @@ static int sg_launch_march2(const SgAdj2Args<T> &m, int nout, cudaStream_t st)
         auto kern = sg_adj_march2_tma_kernel<T, P, SG_M2_G2, SG_M2_RTMAX, SG_M2_NS>;
         const size_t smem = sizeof(T) * SG_M2_NS * SG_M2_RTMAX * 128;
         SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (g_sg_prof_on) cudaEventRecord(g_sg_prof_ev[0], st);
         kern<<<grid, 160, smem, st>>>(m);                                   // 4 consumer warps + 1 producer warp
+        if (g_sg_prof_on) { cudaEventRecord(g_sg_prof_ev[1], st); g_sg_prof_recorded = 1; }
         // tiles with more rows than the ring holds (normally none: one idle launch)
         sg_adj_march2_complement_kernel<T, P, SG_M2_G2, SG_M2_RS><<<148 * 4, 128, 0, st>>>(m, SG_M2_RTMAX, grid.x, grid.y, grid.z);
         g_sg_launches.fetch_add(2);

@@ -907,6 +907,43 @@ __device__ __forceinline__ void sg_bulk_g2s(void *dst, const void *src, unsigned
                  : "memory");
 }
 
+// Producer-warp primitives: executed by the WHOLE converged warp with warp-uniform operands (which then live in uniform
+// registers); one elected lane issues.  A lane-divergent caller (if (lane == 0) ...) costs ~25 instructions per copy.
+__device__ __forceinline__ void sg_m2_bulk_g2s_elect(uint32_t dst, const void *src, unsigned bytes, uint32_t bar)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+        "}\n" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void sg_m2_expect_tx_elect(uint32_t bar, unsigned bytes)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+        "}\n" ::"r"(bar),
+        "r"(bytes)
+        : "memory");
+}
+__device__ __forceinline__ void sg_m2_mbar_wait_u(uint32_t bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SG_M2_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SG_M2_DONE_%=;\n"
+        "bra SG_M2_WAIT_%=;\n"
+        "SG_M2_DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
 __device__ __forceinline__ void sg_mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sg_smem_u32(bar)) : "memory");
@@ -1016,16 +1053,24 @@ __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_
     if (is_producer) {
         // The producer starts feeding the ring at once and runs through the whole chunk on its own; it never meets the
         // consumers at a block-wide barrier (they stage their tables behind a named barrier of their own).
-        if (tid == CW && n_rows > 0) {                                  // one elected lane
+        if (n_rows > 0) {                                               // whole warp, converged; one elected lane issues
+            const uint32_t xs_u = sg_smem_u32(xs), full_u = sg_smem_u32(full), empty_u = sg_smem_u32(empty);
+            int ra[G2], rn[G2];
+#pragma unroll
+            for (int g = 0; g < G2; ++g) { ra[g] = row0[g] - r_first; rn[g] = row0[g + 1] - row0[g]; }
+            const unsigned stage_tx = row_bytes * (unsigned)n_rows;
             for (int p = 0; p < np_total; ++p) {
-                if (p >= NS) sg_mbar_wait(&empty[st], ph ^ 1u);         // every consumer warp has read the previous plane in this stage
-                sg_mbar_expect_tx(&full[st], row_bytes * (unsigned)n_rows);
+                if (p >= NS) sg_m2_mbar_wait_u(empty_u + (uint32_t)st * 8u, ph ^ 1u);   // every consumer warp has read this stage's previous plane
+                const uint32_t fb = full_u + (uint32_t)st * 8u;
+                sg_m2_expect_tx_elect(fb, stage_tx);
                 const T *src = xtile + plane * (int64_t)p;
-                T *dst = xs + (size_t)st * RTMAX * CW;
+                const uint32_t dst = xs_u + (uint32_t)st * (uint32_t)(RTMAX * CW * sizeof(T));
 #pragma unroll
                 for (int g = 0; g < G2; ++g) {
-                    const int ra = row0[g] - r_first, rb = row0[g + 1] - r_first;
-                    for (int r = ra; r < rb; ++r) sg_bulk_g2s(dst + (g * RS5 + (r - ra)) * CW, src + a.n1 * (int64_t)r, row_bytes, &full[st]);
+#pragma unroll
+                    for (int q = 0; q < RS5; ++q)
+                        if (q < rn[g])                                  // warp-uniform
+                            sg_m2_bulk_g2s_elect(dst + (uint32_t)((g * RS5 + q) * CW * sizeof(T)), src + a.n1 * (int64_t)(ra[g] + q), row_bytes, fb);
                 }
                 if (++st == NS) { st = 0; ph ^= 1u; }
             }
