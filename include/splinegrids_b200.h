@@ -202,6 +202,20 @@ int sg_allreduce_sum_f64(double *buf, int64_t count, sg_comm *comm, void *stream
  * (all ranks then synchronise on the stream -- barrier supplied by the host framework --)
  * sg_exchange_reduce: grad[:, k, o] = sum over ranks r whose support covers plane k of stage[r][o][k-k0_r][:],
  *                     summed in rank order (deterministic); k0s / nps are HOST arrays of length world. */
+/* sg_evaluate_adjoint_push: sg_evaluate_adjoint followed by sg_exchange_push of the result, as ONE call.  When the
+ * 3-D double-march pipeline runs, its last kernel stores every finished control plane of the support straight into the
+ * peers' staging slots (peer-to-peer stores overlapping the computation; no separate push kernel); other pipelines
+ * run the push kernel afterwards.  Either way the staging buffers hold what sg_exchange_push would have written. */
+int sg_evaluate_adjoint_push_f32(float *control_points, int nin, const int64_t *n_samples, const int64_t *n_cp, int nout,
+                                 const float *const *tables, const int32_t *const *sample_indices, const int *degree,
+                                 const int *max_derivative_order, const int *derivative_order, const float *eval,
+                                 const float *weights, void *workspace, size_t workspace_bytes, void *const *peer_stage,
+                                 int world, int my_rank, int64_t k0, int64_t np, int64_t max_planes, void *stream);
+int sg_evaluate_adjoint_push_f64(double *control_points, int nin, const int64_t *n_samples, const int64_t *n_cp, int nout,
+                                 const double *const *tables, const int32_t *const *sample_indices, const int *degree,
+                                 const int *max_derivative_order, const int *derivative_order, const double *eval,
+                                 const double *weights, void *workspace, size_t workspace_bytes, void *const *peer_stage,
+                                 int world, int my_rank, int64_t k0, int64_t np, int64_t max_planes, void *stream);
 int sg_exchange_push_f32(const float *grad, void *const *peer_stage, int world, int my_rank, int64_t plane_elems,
                          int64_t c_last, int nout, int64_t k0, int64_t np, int64_t max_planes, void *stream);
 int sg_exchange_push_f64(const double *grad, void *const *peer_stage, int world, int my_rank, int64_t plane_elems,

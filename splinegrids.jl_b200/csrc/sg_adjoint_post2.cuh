@@ -25,7 +25,8 @@ template <typename T, int P, int G2>
 __global__ void __launch_bounds__(128, 5) sg_adj_post2_kernel(T *__restrict__ cp, const T *__restrict__ Pp, const T *__restrict__ table1,
                                                            const int32_t *__restrict__ index1, const int32_t *__restrict__ g_lo,
                                                            const T *__restrict__ g_w, const SgAdjointHeader *hdr, int64_t n1, int64_t c1, int64_t c2, int64_t c3, int P1,
-                                                           int tiles2, int G3, int chunks3, int path)
+                                                           int tiles2, int G3, int chunks3, int path,
+                                                           const __grid_constant__ SgPushSpec push)
 {
     constexpr int S = G2 + P;
     constexpr int JMAX = SG_POST2_JMAX;
@@ -163,5 +164,22 @@ __global__ void __launch_bounds__(128, 5) sg_adj_post2_kernel(T *__restrict__ cp
 #pragma unroll
         for (int q = 0; q < G2; ++q)
             if (i2_0 + q < c2) out[c1 * q] = acc[q];
+        // Fused gradient push (slab-sharded grids): control plane i3 is plane l = i3 - (sf - P) of this rank's support;
+        // it goes into this rank's slot of every rank's staging buffer with peer-to-peer stores (256 contiguous bytes per
+        // warp and row), overlapping the rest of the kernel.  sg_exchange_reduce sums the slots after the barrier.
+        if (push.world > 0) {
+            const int64_t l = i3 - (sf - P);
+            if (l >= 0 && l < push.max_planes) {
+                const int64_t plane_elems = c1 * c2;
+                const int64_t off = push.max_planes * plane_elems * (o + (int64_t)gridDim.z * push.my_rank) + plane_elems * l + i1 + c1 * i2_0;
+#pragma unroll 1
+                for (int r = 0; r < push.world; ++r) {
+                    T *__restrict__ st = static_cast<T *>(push.stage[r]) + off;
+#pragma unroll
+                    for (int q = 0; q < G2; ++q)
+                        if (i2_0 + q < c2) st[c1 * q] = acc[q];
+                }
+            }
+        }
     }
 }

@@ -11,6 +11,8 @@
 std::atomic<int64_t> g_sg_launches{0};
 int g_sg_policy = 0;
 const char *g_sg_last_variant = "none";
+thread_local const SgPushSpec *g_sg_push = nullptr;
+thread_local bool g_sg_push_done = false;
 
 extern "C" int sg_version(void) { return 100; /* 0.1.0 */ }
 

@@ -88,6 +88,18 @@ static inline int sg_fill_grid_args(SgGridArgs<T> &a, int nin, const int64_t *n_
     return SG_OK;
 }
 
+// Fused gradient push of a slab-sharded adjoint (sg_evaluate_adjoint_push_*, sg_exchange.cu): the last kernel of the
+// adjoint stores the control planes of this rank's support straight into this rank's slot of EVERY peer's staging buffer
+// (peer-to-peer stores over NVLink), so the transfer overlaps the computation and no separate push kernel runs.
+#define SG_MAX_PEERS 16
+struct SgPushSpec {
+    void *stage[SG_MAX_PEERS];   // staging buffer of every rank (peer-mapped), layout [world][nout][max_planes][plane_elems]
+    int world, my_rank;          // world == 0: no push
+    long long max_planes;
+};
+extern thread_local const SgPushSpec *g_sg_push;   // set around sg_evaluate_adjoint_impl by the push entry point
+extern thread_local bool g_sg_push_done;           // the pipeline that ran did the push itself
+
 // Adjoint workspace header (first 256 bytes of the workspace)
 struct SgAdjointHeader {
     int nonmonotone;  // set to 1 by the prep kernel if any dimension's span indices decrease

@@ -183,6 +183,9 @@ static int sg_evaluate_adjoint_impl(T *cp, int nin, const int64_t *n_samples, co
     return rc;
 }
 
+extern "C" int sg_exchange_push_f32(const float *, void *const *, int, int, int64_t, int64_t, int, int64_t, int64_t, int64_t, void *);
+extern "C" int sg_exchange_push_f64(const double *, void *const *, int, int, int64_t, int64_t, int, int64_t, int64_t, int64_t, void *);
+
 #define SG_DEFINE_EVAL_API(T, SUF)                                                                                   \
     extern "C" int sg_evaluate_##SUF(T *eval, int nin, const int64_t *n_samples, const int64_t *n_cp, int nout,      \
                                      const T *const *tables, const int32_t *const *indices, const int *degree,       \
@@ -199,6 +202,30 @@ static int sg_evaluate_adjoint_impl(T *cp, int nin, const int64_t *n_samples, co
     {                                                                                                                \
         return sg_evaluate_adjoint_impl<T>(cp, nin, n_samples, n_cp, nout, tables, indices, degree, mdo, der, eval,  \
                                            weights, workspace, workspace_bytes, stream);                             \
+    }                                                                                                                \
+    extern "C" int sg_evaluate_adjoint_push_##SUF(T *cp, int nin, const int64_t *n_samples, const int64_t *n_cp,     \
+                                                  int nout, const T *const *tables, const int32_t *const *indices,   \
+                                                  const int *degree, const int *mdo, const int *der, const T *eval,  \
+                                                  const T *weights, void *workspace, size_t workspace_bytes,         \
+                                                  void *const *peer_stage, int world, int my_rank, int64_t k0,       \
+                                                  int64_t np, int64_t max_planes, void *stream)                      \
+    {                                                                                                                \
+        if (!peer_stage || world < 1 || world > SG_MAX_PEERS || my_rank < 0 || my_rank >= world || nin < 1)          \
+            return SG_ERR_INVALID_ARGUMENT;                                                                          \
+        SgPushSpec spec{};                                                                                           \
+        for (int r = 0; r < world; ++r) spec.stage[r] = peer_stage[r];                                               \
+        spec.world = world; spec.my_rank = my_rank; spec.max_planes = max_planes;                                    \
+        g_sg_push = &spec; g_sg_push_done = false;                                                                   \
+        int rc = sg_evaluate_adjoint_impl<T>(cp, nin, n_samples, n_cp, nout, tables, indices, degree, mdo, der,      \
+                                             eval, weights, workspace, workspace_bytes, stream);                     \
+        g_sg_push = nullptr;                                                                                         \
+        if (rc == SG_OK && !g_sg_push_done) {   /* another pipeline ran: separate push kernel */                     \
+            int64_t plane_elems = 1;                                                                                 \
+            for (int d = 0; d + 1 < nin; ++d) plane_elems *= n_cp[d];                                                \
+            rc = sg_exchange_push_##SUF(cp, peer_stage, world, my_rank, plane_elems, n_cp[nin - 1], nout, k0, np,    \
+                                        max_planes, stream);                                                         \
+        }                                                                                                            \
+        return rc;                                                                                                   \
     }
 
 SG_DEFINE_EVAL_API(float, f32)

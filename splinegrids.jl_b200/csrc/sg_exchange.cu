@@ -12,8 +12,6 @@
 
 #include "sg_common.cuh"
 
-#define SG_MAX_PEERS 16
-
 template <typename T>
 struct SgPeerPtrs {
     T *stage[SG_MAX_PEERS];

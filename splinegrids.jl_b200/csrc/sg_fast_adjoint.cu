@@ -620,10 +620,12 @@ static int sg_run_march2(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &s
         // halo combine + contraction of dimension 1 in one kernel (sg_adjoint_post2.cuh): the partials are read once and
         // the (n1, c2, c3) intermediate never goes to HBM
         dim3 pgrid((unsigned)((mp.tiles2 + 1) * sg_blocks(a.n_cp[0], 128)), (unsigned)m.c3, (unsigned)a.nout);
+        SgPushSpec ps{};                                                // world == 0: plain adjoint
+        if (g_sg_push != nullptr) { ps = *g_sg_push; g_sg_push_done = true; }
         switch (P) {
-            case 1: sg_adj_post2_kernel<T, 1, SG_M2_G2><<<pgrid, 128, 0, st>>>(cp, part, a.table[0], a.index[0], ss.g_lo, ss.g_w, hdr, m.n1, a.n_cp[0], m.c2, m.c3, a.degree[0], mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS); break;
-            case 2: sg_adj_post2_kernel<T, 2, SG_M2_G2><<<pgrid, 128, 0, st>>>(cp, part, a.table[0], a.index[0], ss.g_lo, ss.g_w, hdr, m.n1, a.n_cp[0], m.c2, m.c3, a.degree[0], mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS); break;
-            default: sg_adj_post2_kernel<T, 3, SG_M2_G2><<<pgrid, 128, 0, st>>>(cp, part, a.table[0], a.index[0], ss.g_lo, ss.g_w, hdr, m.n1, a.n_cp[0], m.c2, m.c3, a.degree[0], mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS); break;
+            case 1: sg_adj_post2_kernel<T, 1, SG_M2_G2><<<pgrid, 128, 0, st>>>(cp, part, a.table[0], a.index[0], ss.g_lo, ss.g_w, hdr, m.n1, a.n_cp[0], m.c2, m.c3, a.degree[0], mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS, ps); break;
+            case 2: sg_adj_post2_kernel<T, 2, SG_M2_G2><<<pgrid, 128, 0, st>>>(cp, part, a.table[0], a.index[0], ss.g_lo, ss.g_w, hdr, m.n1, a.n_cp[0], m.c2, m.c3, a.degree[0], mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS, ps); break;
+            default: sg_adj_post2_kernel<T, 3, SG_M2_G2><<<pgrid, 128, 0, st>>>(cp, part, a.table[0], a.index[0], ss.g_lo, ss.g_w, hdr, m.n1, a.n_cp[0], m.c2, m.c3, a.degree[0], mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS, ps); break;
         }
         g_sg_launches.fetch_add(1);
         return SG_OK;

@@ -100,6 +100,34 @@ class PeerGradientExchange:
         self.step = 0
         self._prepared = {}
 
+    def adjoint_and_exchange_(self, grid, *, control_points: torch.Tensor, **kw) -> torch.Tensor:
+        """Local ``evaluate_adjoint!`` with the gradient push FUSED into its last kernel
+        (``sg_evaluate_adjoint_push``: finished control planes leave for the peers' staging slots while the kernel is still
+        running), then the barrier and the local reduce.  Same result as ``evaluate_adjoint_`` + ``exchange_``."""
+        from . import _lib
+        b = self.step & 1
+        self.step += 1
+        push = (b, self.peer_ptrs[b], self.world, self.rank, self.k0[self.rank], self.np_[self.rank], self.max_planes)
+        evaluate_adjoint_(grid, control_points=control_points, _push=push, **kw)
+        return self._barrier_and_reduce_(control_points, b, _lib.stream_ptr(self.device))
+
+    def _barrier_and_reduce_(self, grad: torch.Tensor, b: int, st) -> torch.Tensor:
+        from . import _lib
+        C = _lib.C
+        key = ("reduce", b, grad.data_ptr())
+        prep = self._prepared.get(key)
+        if prep is None:
+            suf = _lib.suffix(self.dtype)
+            prep = (getattr(_lib.lib(), "sg_exchange_reduce_" + suf),
+                    (_lib.ptr(grad), _lib.ptr(self.stage[b]), C.c_int(self.world), self._k0s, self._nps,
+                     C.c_int64(self.plane_elems), C.c_int64(self.c_last), C.c_int(self.nout), C.c_int64(self.max_planes)))
+            if len(self._prepared) >= 16:
+                self._prepared.clear()
+            self._prepared[key] = prep
+        self.hdl[b].barrier(channel=0)                      # stream-ordered, all ranks
+        _lib.check(prep[0](*prep[1], st), "sg_exchange_reduce")
+        return grad
+
     def exchange_(self, grad: torch.Tensor) -> torch.Tensor:
         from . import _lib
         C = _lib.C
@@ -141,6 +169,7 @@ class SlabShardedGrid:
         self.global_dims = tuple(global_dims)
         self.rank, self.world_size, self.group = rank, world_size, group
         self.exchange = None
+        self.fused_push = True        # push fused into the adjoint's last kernel (False: separate push kernel)
         self.exchange_kind = "none" if world_size == 1 else "nccl_allreduce"
         n_last = self.global_dims[-1].n_sample_points
         assert n_last >= world_size, "fewer sample rows along the slowest axis than ranks"
@@ -150,7 +179,7 @@ class SlabShardedGrid:
         if peer_exchange and world_size > 1:
             try:
                 self.exchange = PeerGradientExchange(self.global_dims, Nout, rank, world_size, group)
-                self.exchange_kind = "peer_memory_push_reduce"
+                self.exchange_kind = "peer_memory_push_reduce (push fused into the adjoint's last kernel)"
             except Exception as e:   # symmetric memory unavailable: keep the NCCL all-reduce
                 import warnings
                 warnings.warn(f"peer-memory gradient exchange unavailable ({e!r}); using the NCCL all-reduce")
@@ -166,8 +195,11 @@ class SlabShardedGrid:
     def evaluate_adjoint_(self, *, control_points: Optional[torch.Tensor] = None, **kw) -> None:
         """Local ``evaluate_adjoint!`` followed by the gradient all-reduce; afterwards every rank holds the
         full gradient, exactly what the single-device call produces (up to summation order)."""
-        evaluate_adjoint_(self.local, control_points=control_points, **kw)
         cp = obtain(self.local.control_points if control_points is None else control_points)
+        if self.exchange is not None and self.fused_push:
+            self.exchange.adjoint_and_exchange_(self.local, control_points=cp, **kw)
+            return
+        evaluate_adjoint_(self.local, control_points=control_points, **kw)
         if self.exchange is not None:
             self.exchange.exchange_(cp)
         else:

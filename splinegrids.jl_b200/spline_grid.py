@@ -208,7 +208,7 @@ def _workspace(grid: SplineGrid) -> torch.Tensor:
 
 
 def evaluate_adjoint_(obj, *, derivative_order: Optional[Sequence[int]] = None, control_points=None,
-                      eval=None, allow_nurbs: bool = False, _retry: bool = False) -> None:
+                      eval=None, allow_nurbs: bool = False, _retry: bool = False, _push=None) -> None:
     """``evaluate_adjoint!`` -- src/adjoint.jl:52-83 (K4) for a grid; src/adjoint.jl:172-205 for control
     points.  Overwrites ``control_points`` (zero fill first, :61) with the adjoint applied to ``eval``.
 
@@ -225,15 +225,22 @@ def evaluate_adjoint_(obj, *, derivative_order: Optional[Sequence[int]] = None, 
     control_points = grid.control_points if control_points is None else control_points
     eval_ = grid.eval if eval is None else eval
     cp = obtain(control_points)
-    key = _prepared_key("adj", grid, der, cp, eval_)
+    # _push = (tag, peer_ptrs, world, rank, k0, np, max_planes): fused gradient push (distributed.PeerGradientExchange)
+    key = _prepared_key("adj" if _push is None else ("adj_push", _push[0]), grid, der, cp, eval_)
     prep = grid.__dict__.get("_prepared", {}).get(key)
     if prep is None:
         validate_partial_derivatives(grid.spline_dimensions, der, is_nurbs=grid.is_nurbs())
         cp = _check_arrays(grid, control_points, eval_)
         ws = _workspace(grid)
-        fn = getattr(_lib.lib(), "sg_evaluate_adjoint_" + _lib.suffix(grid.dtype))
-        prep = (fn, (_lib.ptr(cp), *_grid_call_args(grid, der), _lib.ptr(eval_), _lib.ptr(grid.weights), _lib.ptr(ws),
-                     C.c_size_t(ws.numel())), grid.device.index, ws)
+        args = (_lib.ptr(cp), *_grid_call_args(grid, der), _lib.ptr(eval_), _lib.ptr(grid.weights), _lib.ptr(ws),
+                C.c_size_t(ws.numel()))
+        if _push is None:
+            fn = getattr(_lib.lib(), "sg_evaluate_adjoint_" + _lib.suffix(grid.dtype))
+        else:
+            fn = getattr(_lib.lib(), "sg_evaluate_adjoint_push_" + _lib.suffix(grid.dtype))
+            _, peer_ptrs, world, rank, k0, np_, max_planes = _push
+            args = args + (peer_ptrs, C.c_int(world), C.c_int(rank), C.c_int64(k0), C.c_int64(np_), C.c_int64(max_planes))
+        prep = (fn, args, grid.device.index, ws)
         _prepared_store(grid, key, prep)
     fn, args, dev_index = prep[0], prep[1], prep[2]
     if torch.cuda.current_device() == dev_index:
@@ -244,7 +251,7 @@ def evaluate_adjoint_(obj, *, derivative_order: Optional[Sequence[int]] = None, 
     if status == -3 and not _retry:            # SG_ERR_WORKSPACE: the pipeline choice (tuning environment) changed since
         grid.__dict__.get("_prepared", {}).pop(key, None)   # the call was prepared -> size the workspace again
         return evaluate_adjoint_(obj, derivative_order=derivative_order, control_points=control_points, eval=eval,
-                                 allow_nurbs=allow_nurbs, _retry=True)
+                                 allow_nurbs=allow_nurbs, _retry=True, _push=_push)
     _lib.check(status, "sg_evaluate_adjoint")
     after_launch(grid.device)
     return None

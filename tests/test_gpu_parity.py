@@ -455,6 +455,62 @@ def test_peer_exchange_kernels_single_device(S, ft):
         assert torch.equal(dev[r], dev[0])                          # rank-order summation: bit-identical on every rank
 
 
+@pytest.mark.parametrize("shape", [((12, 9, 40), (2, 3, 3), (128, 40, 96), "adjoint_march2"),
+                                   ((9, 8, 40), (3, 2, 3), (40, 36, 96), "adjoint_passes")], ids=["fused", "fallback"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_fused_gradient_push_single_device(S, world, shape):
+    """sg_evaluate_adjoint_push with every "rank" simulated on one device (peer pointers = local buffers): after all
+    ranks' calls, every staging buffer holds exactly what adjoint + sg_exchange_push writes, and the reduce gives the
+    full-grid gradient.  "fused": the double march's post kernel does the peer stores itself; "fallback": another
+    pipeline runs, followed by the separate push kernel inside the same C call."""
+    import ctypes as C
+    from gpu_helpers import oracle_adjoint
+    lib = S._lib.lib()
+    rng = np.random.default_rng(14)
+    n_cp, deg, n_s, variant = shape
+    nout = 2
+    gdims = tuple(S.SplineDimension(c, p, n, float_type="Float64") for c, p, n in zip(n_cp, deg, n_s))
+    full = S.SplineGrid(gdims, nout)
+    e = np.asfortranarray(rng.random(n_s + (nout,)))
+    ref_grad = oracle_adjoint(full, e)
+    idx3 = S.to_numpy(gdims[2].sample_indices)
+    shards = [S.SlabShardedGrid(gdims, nout, r, world) for r in range(world)]
+    k0 = [int(idx3[sh.lo]) - deg[2] - 1 for sh in shards]
+    npl = [int(idx3[sh.hi - 1]) - k for sh, k in zip(shards, k0)]
+    max_planes, plane = max(npl), n_cp[0] * n_cp[1]
+    slot = world * nout * max_planes * plane
+
+    def run(fused):
+        stages = [torch.full((slot,), float("nan"), dtype=torch.float64, device="cuda") for _ in range(world)]
+        peer = (C.c_void_p * world)(*[t.data_ptr() for t in stages])
+        grads = []
+        for r, sh in enumerate(shards):
+            g = torch.full_like(sh.local.control_points.obtain(), 3.0)
+            ein = S.to_device(e[:, :, sh.lo:sh.hi, :])
+            if fused:
+                S.evaluate_adjoint_(sh.local, eval=ein, control_points=g,
+                                    _push=(("t", r), peer, world, r, k0[r], npl[r], max_planes))
+                assert S.last_variant() == variant
+            else:
+                S.evaluate_adjoint_(sh.local, eval=ein, control_points=g)
+                S._lib.check(lib.sg_exchange_push_f64(S._lib.ptr(g), peer, C.c_int(world), C.c_int(r), C.c_int64(plane),
+                                                      C.c_int64(n_cp[2]), C.c_int(nout), C.c_int64(k0[r]), C.c_int64(npl[r]),
+                                                      C.c_int64(max_planes), None), "push")
+            grads.append(g)
+        torch.cuda.synchronize()
+        return stages, grads
+
+    st_fused, grads = run(True)
+    st_plain, _ = run(False)
+    for a, b in zip(st_fused, st_plain):
+        assert torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0))   # same slots written, same bits
+    for r in range(world):
+        S._lib.check(lib.sg_exchange_reduce_f64(S._lib.ptr(grads[r]), S._lib.ptr(st_fused[r]), C.c_int(world),
+                                                S._lib.i64_array(k0), S._lib.i64_array(npl), C.c_int64(plane),
+                                                C.c_int64(n_cp[2]), C.c_int(nout), C.c_int64(max_planes), None), "reduce")
+        assert rel_err(S.to_numpy(grads[r]), ref_grad) <= 1e-12
+
+
 def test_nurbs_adjoint_is_transpose_of_forward(S):
     """The NURBS adjoint has no reference behaviour (src/adjoint.jl:52-57): pin it as the exact transpose of our
     own forward map via <R p, e> = <p, R' e>, and as the plain adjoint when all weights are 1."""
