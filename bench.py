@@ -181,6 +181,12 @@ def main_gpu(args):
     import torch
     import torch.distributed as dist
 
+    # Libraries print to stdout while we run (NCCL's version banner, for one); the contract is ONE JSON line there, so
+    # everything else is sent to stderr and the line is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import __graft_entry__ as entry
     S = entry.load_package()                       # fails loudly if libsplinegrids_b200.so is missing
     rank = int(os.environ.get("RANK", "0"))
@@ -438,7 +444,8 @@ def main_gpu(args):
                            "l2": "inputs/outputs (1.07 GB per op) exceed the 126 MB L2; no flush needed"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "ops": ops,
                 "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0
