@@ -66,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                          "-lms", "25", "-i", str(self.gpu_index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -75,12 +75,20 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def wait_first_sample(self, timeout=2.0):
+        """nvidia-smi needs a few hundred ms to start: do not begin the timed region before it samples."""
+        t_end = time.perf_counter() + timeout
+        while self.proc is not None and not self.lines and time.perf_counter() < t_end:
+            time.sleep(0.01)
+
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples received between host times t0 and t1 (the timed region); if the region was shorter
+        than the sampling interval, the samples closest to it."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.06)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -88,7 +96,15 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        stamped = list(self.lines)
+        if t0 is not None and t1 is not None:
+            inside = [ln for ts, ln in stamped if t0 <= ts <= t1 + 0.03]
+            if not inside and stamped:               # region shorter than the interval: first sample after it began
+                after = [ln for ts, ln in stamped if ts >= t0]
+                inside = after[:1] if after else [stamped[-1][1]]
+        else:
+            inside = [ln for _, ln in stamped]
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -267,9 +283,11 @@ def main_gpu(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_first_sample()
     S.launch_count_reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_host0 = time.perf_counter()
     e0.record()
     if cap is not None:
         for _ in range(args.steps // 2):
@@ -281,9 +299,10 @@ def main_gpu(args):
             step()
     e1.record()
     barrier()
+    t_host1 = time.perf_counter()
     ms_total = e0.elapsed_time(e1)
     launches = S.launch_count() + (cap.kernel_launches * (args.steps // 2) if cap is not None else 0)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_host0, t_host1) if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -454,7 +473,7 @@ def main_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-planes", type=int, default=32, help="slab thickness of the bounded CPU sample")
