@@ -126,6 +126,17 @@ for (Tv, suf) in ((Float32, "f32"), (Float64, "f64"))
     end
 end
 
+# Slab-sharded multi-GPU adjoint (no counterpart in the reference, SURVEY.md 8e): one task per GPU holds the slab
+#   (sliced last-dimension arrays); `peer_stage` = the ranks' staging buffers mapped into this process (CUDA IPC /
+#   CUDA.jl peer access), `k0`/`np` = first control plane / number of planes of this slab's support.
+#   sg_evaluate_adjoint_push_f64(cp, <same arguments as sg_evaluate_adjoint_f64>, peer_stage::Ptr{Ptr{Cvoid}},
+#                                world::Cint, my_rank::Cint, k0::Int64, np::Int64, max_planes::Int64, stream)
+#       adjoint whose last kernel stores the finished control planes into every peer's staging slot (NVLink P2P);
+#   <barrier across the ranks on the stream>;
+#   sg_exchange_reduce_f64(cp, my_stage, world, k0s::Ptr{Int64}, nps::Ptr{Int64}, plane_elems, c_last, Nout,
+#                          max_planes, stream)   -> every rank holds the full gradient (rank-order sum, deterministic).
+# A whole iteration (evaluate!, evaluate_adjoint!) can be wrapped in CUDA.@captured: the library only enqueues work.
+
 # K7 / K8 (src/control_points.jl:296-349, src/adjoint.jl:154-205) are reached through the unchanged Julia level loops
 # of evaluate!(::LocallyRefinedControlPoints) / evaluate_adjoint!(…): override the two kernel launches the same
 # way with sg_scatter_active_* / sg_gather_zero_active_* (argument lists in include/splinegrids_b200.h).
