@@ -699,8 +699,10 @@ __global__ void __launch_bounds__(128) sg_adj_tile_combine_kernel(T *__restrict_
 // a span, over its rows), then marches dimension 3 with the usual P+1 live planes per slot: acc3[S][P+1].
 // When span 3 advances, S completed values leave per thread.  No shared-memory exchange, no atomics; the
 // only block-level sync is the staging of the (CTA-uniform) table rows.
-// Output: partial[j1][slot S][tile2][row3 G3+P][chunk3][o]  (tile/chunk halos are summed by the combine
-// kernel).  For C3 the pass writes ~130 MB instead of the 268 + 67 MB of the two separate passes.
+// Output: partial[j1][slot S][tile2][row3 G3+P][chunk3][o]; the tile/chunk halos are summed -- and dimension 1 is
+// contracted -- by sg_adj_post2_kernel (sg_adjoint_post2.cuh).  For C3 the pass writes 135 MB instead of the
+// 268 + 67 MB of two separate passes.  The chunks of dimension 3 adapt on device to the spans that hold samples
+// (sg_m2_chunk_len); a.G3 is only the row stride of a chunk in the partials.
 // Rows of a span are processed RS at a time (any number of samples per span works).
 // =============================================================================================
 // Chunks of dimension 3 adapt to the spans that really hold samples (a slab of a sharded grid touches few of them):
