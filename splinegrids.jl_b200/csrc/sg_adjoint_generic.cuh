@@ -11,12 +11,6 @@
 template <typename T>
 struct SgSpanStarts {
     int32_t *start[SG_MAX_DIMS];
-    // fused adjoint: per warp tile of `tile_size` samples of dimension 1: first control index (0-based)
-    // and number of control indices touched (slots)
-    int32_t *tile_lo;
-    int32_t *tile_ni;
-    int tile_size;
-    int n_tiles;
     // gather table of dimension 1 (used by the double march's post kernel): for every control index i the first sample
     // of its support, the number of samples, and the first SG_GATHER_RMAX basis weights B1[lo + r, i - span + p]
     int32_t *g_lo;     // [c_1][2] = (lo, len)
@@ -84,17 +78,6 @@ __global__ void sg_adjoint_prep_kernel(const __grid_constant__ SgGridArgs<T> a, 
             if (idx[mid] >= s) hi = mid; else lo = mid + 1;
         }
         ss.start[d][s] = (int32_t)lo;
-    }
-    if (d == 0 && ss.tile_lo != nullptr) {
-        const int p = a.degree[0];
-        for (int64_t t = tid; t < ss.n_tiles; t += stride) {
-            const int64_t j0 = t * ss.tile_size;
-            const int64_t j1 = min(j0 + ss.tile_size, n) - 1;
-            const int first = idx[j0], last = idx[j1];
-            const int ni = last - first + 1 + p;
-            ss.tile_lo[t] = first - p - 1;
-            ss.tile_ni[t] = ni;     // <= tile_size + p for monotone spans
-        }
     }
 }
 

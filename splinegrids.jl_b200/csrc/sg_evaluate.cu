@@ -42,9 +42,7 @@ static int sg_evaluate_impl(T *eval, int nin, const int64_t *n_samples, const in
 struct SgAdjointLayout {
     size_t header;               // offset 0
     size_t starts[SG_MAX_DIMS];  // int32[n_cp+2] per dimension
-    size_t tile_lo, tile_ni;     // int32[n_tiles] each (fused adjoint)
     size_t g_lo, g_w;            // gather table of dimension 1: int32[c_1][2], T[SG_GATHER_RMAX][c_1]
-    int n_tiles, tile_size;
     size_t denom;                // T[n_total] (rational only), else 0
     size_t fast;                 // scratch of the tiled fast path
     size_t total;
@@ -61,12 +59,6 @@ static SgAdjointLayout sg_adjoint_layout(int nin, const int64_t *n_samples, cons
         off += sg_align256((size_t)(n_cp[d] + 2) * sizeof(int32_t));
         n_total *= n_samples[d];
     }
-    L.tile_size = 32 * (elem_size == 4 ? 4 : 2);
-    L.n_tiles = (int)((n_samples[0] + L.tile_size - 1) / L.tile_size);
-    L.tile_lo = off;
-    off += sg_align256((size_t)L.n_tiles * sizeof(int32_t));
-    L.tile_ni = off;
-    off += sg_align256((size_t)L.n_tiles * sizeof(int32_t));
     L.g_lo = off;
     off += sg_align256((size_t)n_cp[0] * 2 * sizeof(int32_t));
     L.g_w = off;
@@ -130,13 +122,8 @@ static int sg_evaluate_adjoint_impl(T *cp, int nin, const int64_t *n_samples, co
         ss.start[d] = reinterpret_cast<int32_t *>(ws + L.starts[d]);
         max_len = std::max(max_len, std::max(n_samples[d], n_cp[d] + 2));
     }
-    ss.tile_lo = reinterpret_cast<int32_t *>(ws + L.tile_lo);
-    ss.tile_ni = reinterpret_cast<int32_t *>(ws + L.tile_ni);
-    ss.tile_size = L.tile_size;
-    ss.n_tiles = L.n_tiles;
     ss.g_lo = reinterpret_cast<int32_t *>(ws + L.g_lo);
     ss.g_w = reinterpret_cast<T *>(ws + L.g_w);
-    max_len = std::max<int64_t>(max_len, L.n_tiles);
     rc = SG_OK;
     do {
         cudaError_t e = cudaMemsetAsync(hdr, 0, sizeof(SgAdjointHeader), st);

@@ -7,7 +7,6 @@
 #include "sg_evaluate_generic.cuh"
 #include "sg_fast.cuh"
 #include "sg_fast_adjoint.cuh"
-#include "sg_adjoint_march3.cuh"
 #include "sg_adjoint_post2.cuh"
 #include "sg_fast_eval.cuh"
 
@@ -224,65 +223,6 @@ static int sg_run_multipass(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T>
     return SG_OK;
 }
 
-// ---- fused pipeline: plan -----------------------------------------------------------------------------
-struct SgFusedPlan {
-    bool ok;
-    int n_tiles, tile_size, n_slots;
-    int64_t M;                   // product of the middle sample dimensions
-    size_t y_off;                // output of the fused first pass
-    int npassA;                  // middle passes (dims D-2 .. 1)
-    SgAdjPass pass[SG_MAX_DIMS];
-    size_t bytes;
-};
-
-static SgFusedPlan sg_adjoint_fused_plan(int nin, const int64_t *n_samples, const int64_t *n_cp, int nout, const int *degree,
-                                         int elem_size, bool rational)
-{
-    SgFusedPlan fp{};
-    const int V = elem_size == 4 ? 4 : 2;
-    fp.tile_size = 32 * V;
-    fp.ok = false;
-    if (rational || nin < 2 || sg_env_int("SG_ADJ_FUSED", 0) == 0) return fp;
-    if (degree[nin - 1] > 3) return fp;                              // instantiated degrees of the marching axis
-    if (n_samples[0] % fp.tile_size != 0) return fp;
-    fp.n_tiles = (int)(n_samples[0] / fp.tile_size);
-    fp.n_slots = fp.tile_size + SG_ADJ_SLOT_PAD;
-    int64_t inner = 1;
-    for (int e = 0; e < nin - 1; ++e) inner *= n_samples[e];
-    if ((inner / V) * nout < 24576) return fp;                        // too few columns: the chunked multi-pass path is better
-    if (nout > 65535) return fp;
-    fp.M = inner / n_samples[0];
-    size_t off = 0;
-    fp.y_off = off;
-    off += sg_al256((size_t)fp.n_slots * fp.n_tiles * fp.M * n_cp[nin - 1] * nout * elem_size);
-    int64_t outer = (int64_t)nout * n_cp[nin - 1];
-    for (int d = nin - 2; d >= 1; --d) {
-        SgAdjPass &ps = fp.pass[fp.npassA++];
-        ps.d = d;
-        ps.inner = (int64_t)fp.n_slots * fp.n_tiles;
-        for (int e = 1; e < d; ++e) ps.inner *= n_samples[e];
-        ps.n_d = n_samples[d];
-        ps.c_d = n_cp[d];
-        ps.outer = outer;
-        ps.P = degree[d];
-        const int64_t nspans = ps.c_d - ps.P;
-        const int64_t threads = ((ps.inner + V - 1) / V) * outer;
-        int64_t nchunks = 1;
-        if (threads < 65536) nchunks = std::min<int64_t>(nspans, (148 * 8 * 128 + threads - 1) / threads);
-        ps.G = (int)((nspans + nchunks - 1) / nchunks);
-        ps.nchunks = (int)((nspans + ps.G - 1) / ps.G);
-        ps.part_off = off;
-        if (ps.nchunks > 1) off += sg_al256((size_t)ps.inner * (ps.G + ps.P) * ps.nchunks * outer * elem_size);
-        ps.out_off = off;
-        off += sg_al256((size_t)ps.inner * ps.c_d * outer * elem_size);
-        if (ps.outer > 65535 || ps.nchunks > 65535 || (ps.nchunks > 1 && ps.c_d > 65535)) return fp;
-        outer *= ps.c_d;
-    }
-    fp.bytes = off;
-    fp.ok = true;
-    return fp;
-}
-
 // ---- 3-D double-march pipeline ---------------------------------------------------------------------------
 struct SgMarch2Plan {
     bool ok;
@@ -332,217 +272,14 @@ static SgMarch2Plan sg_adjoint_march2_plan(int nin, const int64_t *n_samples, co
 }
 
 
-// ---- 3-D single-pass pipeline (sg_adjoint_march3.cuh) ---------------------------------------------------
-#define SG_M3_DEFAULT_MODE 0   // opt-in until it beats the double march on C3
-struct SgMarch3Plan {
-    bool ok;
-    int P, W, nb1, tiles2, L1, L3, maxseg;
-    size_t smem;
-    size_t mask_off, mask_bytes, part_off, bytes;
-};
-
-static size_t sg_m3_smem_bytes(int elem_size, int P)
-{
-    const size_t S2 = SG_M3_G2 + P;
-    return (size_t)elem_size * ((size_t)SG_M3_NS * SG_M3_G2 * SG_M3_RPT * SG_M3_CW + (size_t)3 * SG_M3_G2 * 4 * SG_M3_CW +
-                                3 * S2 * SG_M3_PITCH + 3 * S2 * 4 * SG_M3_NSPMAX + (size_t)8 * SG_M3_PITCH + (size_t)SG_M3_G2 * SG_M3_RPT * 4 +
-                                (size_t)SG_M3_MAXPL * 4) +
-           sizeof(int) * SG_M3_MAXPL + 128;
-}
-
-template <typename T>
-static const void *sg_m3_kernel_ptr(int P)
-{
-    switch (P) {
-        case 1: return reinterpret_cast<const void *>(&sg_adj_march3_kernel<T, 1>);
-        case 2: return reinterpret_cast<const void *>(&sg_adj_march3_kernel<T, 2>);
-        default: return reinterpret_cast<const void *>(&sg_adj_march3_kernel<T, 3>);
-    }
-}
-
-// resident workers for the persistent grid: SMs x CTAs per SM at this shared-memory size
-static int sg_m3_workers(int elem_size, int P, size_t smem)
-{
-    const int forced = sg_env_int("SG_ADJ_M3_W", 0);
-    if (forced > 0) return forced;
-    int dev = 0, sms = 148, per_sm = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const void *k = elem_size == 4 ? sg_m3_kernel_ptr<float>(P) : sg_m3_kernel_ptr<double>(P);
-    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, SG_M3_THREADS, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
-    return sms * per_sm;
-}
-
-static SgMarch3Plan sg_adjoint_march3_plan(int nin, const int64_t *n_samples, const int64_t *n_cp, int nout, const int *degree,
-                                           int elem_size, bool rational)
-{
-    SgMarch3Plan mp{};
-    mp.ok = false;
-    // SG_ADJ_MARCH3: 0 = never, 1 = whenever the hard constraints hold, 2 = densely sampled grids only (auto rule)
-    const int mode = sg_env_int("SG_ADJ_MARCH3", SG_M3_DEFAULT_MODE);
-    if (rational || nin != 3 || mode == 0) return mp;
-    const int P = degree[1];
-    if (degree[2] != P || P < 1 || P > 3 || degree[0] < 1 || degree[0] > 5) return mp;
-    if ((n_samples[0] * elem_size) % 16 != 0) return mp;                 // bulk copies: 16-byte rows
-    const int64_t nsp1 = n_cp[0] - degree[0], nsp2 = n_cp[1] - P, nsp3 = n_cp[2] - P;
-    const bool forced = mode == 1 || g_sg_policy == 2;
-    if (!forced) {
-        if (n_samples[0] < 2 * SG_M3_CW) return mp;
-        if (n_samples[1] < nsp2 || n_samples[2] < nsp3) return mp;       // sparse sampling: the partial buffer would dominate
-        if (degree[0] > 3 || n_samples[0] < nsp1) return mp;               // dimension 1: fast contraction only
-        if (n_samples[1] > 2 * SG_M3_RPT * nsp2) return mp;               // many rows per span: several passes, other pipelines win
-    }
-    mp.P = P;
-    mp.nb1 = (int)((n_samples[0] + SG_M3_CW - 1) / SG_M3_CW);
-    mp.tiles2 = (int)((nsp2 + SG_M3_G2 - 1) / SG_M3_G2);
-    const int64_t ncols = (int64_t)nout * mp.nb1 * mp.tiles2;
-    if (n_cp[1] > 65535 || n_cp[2] * nout > 65535 || ncols > (1 << 24) || mp.tiles2 > SG_M3_MAXTILES) return mp;
-    mp.smem = sg_m3_smem_bytes(elem_size, P);
-    mp.W = sg_m3_workers(elem_size, P, mp.smem);
-    if (mp.W <= 0) return mp;
-    // small problems: at least ~4 planes per worker and at most ~8 segments per (block, tile) column
-    const int64_t col_equiv = std::max<int64_t>(1, (int64_t)nout * mp.nb1 * nsp2 / SG_M3_G2);
-    mp.W = (int)std::min<int64_t>(mp.W, std::max<int64_t>(1, std::min<int64_t>(col_equiv * 8, col_equiv * n_samples[2] / 4)));
-    // segments per (block, tile) column: a tile of G2 spans holds ~G2/nsp2 of the rows of its column block, which is
-    // shared by W / (nout*nb1) workers; x2 for uneven knot spans.  Columns that need more fall back on device.
-    mp.maxseg = (int)((2 * (int64_t)mp.W * SG_M3_G2 + (int64_t)nout * mp.nb1 * nsp2 - 1) / ((int64_t)nout * mp.nb1 * nsp2)) + 3;
-    mp.maxseg = std::min(mp.maxseg, 32);                                  // bits of the row mask
-    mp.L1 = (int)(n_cp[0] + (int64_t)mp.nb1 * (degree[0] + 1));
-    mp.L3 = (int)(n_cp[2] + (int64_t)mp.maxseg * (P + 1));
-    size_t off = 0;
-    mp.mask_off = off;
-    mp.mask_bytes = (size_t)ncols * n_cp[2] * sizeof(unsigned);
-    off += sg_al256(mp.mask_bytes);
-    mp.part_off = off;
-    off += sg_al256((size_t)mp.L1 * (SG_M3_G2 + P) * mp.tiles2 * mp.L3 * nout * elem_size);
-    mp.bytes = off;
-    mp.ok = true;
-    return mp;
-}
-
-typedef CUresult (*SgEncodeTiledFn3)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static SgEncodeTiledFn3 sg_m3_encoder()
-{
-    static SgEncodeTiledFn3 fn = [] {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-            p = nullptr;
-        return reinterpret_cast<SgEncodeTiledFn3>(p);
-    }();
-    return fn;
-}
-
-// eval as a 3-D tensor (n1, n2, n3*nout), boxes (CW, 16 >> i, 1)
-template <typename T>
-static bool sg_m3_make_maps(SgM3Maps &maps, const T *eval, int64_t n1, int64_t n2, int64_t n3nout)
-{
-    SgEncodeTiledFn3 enc = sg_m3_encoder();
-    if (!enc) return false;
-    cuuint64_t dims[3] = {(cuuint64_t)n1, (cuuint64_t)n2, (cuuint64_t)n3nout};
-    cuuint64_t strides[2] = {(cuuint64_t)n1 * sizeof(T), (cuuint64_t)n1 * n2 * sizeof(T)};
-    cuuint32_t estr[3] = {1, 1, 1};
-    const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-    for (int i = 0; i < SG_M3_NMAPS; ++i) {
-        cuuint32_t box[3] = {SG_M3_CW, (cuuint32_t)(16 >> i), 1};
-        if (enc(&maps.m[i], dt, 3, const_cast<T *>(eval), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return false;
-    }
-    return true;
-}
-
-template <typename T>
-static int sg_run_march3(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &ss, SgAdjointHeader *hdr, const T *eval,
-                         const SgMarch3Plan &mp, char *ws, cudaStream_t st)
-{
-    SgAdj3Args<T> m{};
-    m.X = eval;
-    m.part = reinterpret_cast<T *>(ws + mp.part_off);
-    m.rowmask = reinterpret_cast<unsigned *>(ws + mp.mask_off);
-    m.table1 = a.table[0]; m.table2 = a.table[1]; m.table3 = a.table[2];
-    m.index1 = a.index[0]; m.index3 = a.index[2];
-    m.start1 = ss.start[0]; m.start2 = ss.start[1];
-    m.hdr = hdr;
-    m.n1 = a.n_samples[0]; m.n2 = a.n_samples[1]; m.n3 = a.n_samples[2];
-    m.c1 = a.n_cp[0]; m.c2 = a.n_cp[1]; m.c3 = a.n_cp[2];
-    m.P1 = a.degree[0];
-    m.nb1 = mp.nb1; m.tiles2 = mp.tiles2; m.nout = a.nout;
-    m.L1 = mp.L1; m.L3 = mp.L3; m.maxseg = mp.maxseg;
-    SgM3Maps maps;
-    if (!sg_m3_make_maps<T>(maps, eval, m.n1, m.n2, m.n3 * a.nout)) return SG_ERR_UNSUPPORTED;
-    SG_CUDA(cudaMemsetAsync(m.rowmask, 0, mp.mask_bytes, st));
-    switch (mp.P) {
-        case 1: sg_adj_march3_kernel<T, 1><<<mp.W, SG_M3_THREADS, mp.smem, st>>>(m, maps); break;
-        case 2: sg_adj_march3_kernel<T, 2><<<mp.W, SG_M3_THREADS, mp.smem, st>>>(m, maps); break;
-        default: sg_adj_march3_kernel<T, 3><<<mp.W, SG_M3_THREADS, mp.smem, st>>>(m, maps); break;
-    }
-    dim3 cgrid(sg_blocks(m.c1, 128), (unsigned)m.c2, (unsigned)(m.c3 * a.nout));
-    sg_adj_combine3_kernel<T><<<cgrid, 128, 0, st>>>(cp, m.part, m.rowmask, hdr, m.index1, m.n1, m.c1, m.c2, m.c3, m.P1, mp.P, SG_M3_G2,
-                                                     mp.nb1, mp.tiles2, mp.L1, mp.L3);
-    g_sg_launches.fetch_add(2);
-    return SG_OK;
-}
-
 size_t sg_adjoint_fast_scratch_bytes(int nin, const int64_t *n_samples, const int64_t *n_cp, int nout, const int *degree,
                                      int elem_size)
 {
     if (!sg_adjoint_fast_supported(nin, degree, false)) return 0;
     const size_t a = sg_adjoint_plan(nin, n_samples, n_cp, nout, degree, elem_size).bytes;
-    const SgFusedPlan fp = sg_adjoint_fused_plan(nin, n_samples, n_cp, nout, degree, elem_size, false);
     const SgMarch2Plan mp = sg_adjoint_march2_plan(nin, n_samples, n_cp, nout, degree, elem_size, false);
-    const SgMarch3Plan m3 = sg_adjoint_march3_plan(nin, n_samples, n_cp, nout, degree, elem_size, false);
     // the pipelines never run together: they share the scratch
-    return std::max(std::max(std::max(a, fp.ok ? fp.bytes : (size_t)0), mp.ok ? mp.bytes : (size_t)0), m3.ok ? m3.bytes : (size_t)0);
-}
-
-template <typename T, int P>
-static void sg_launch_fused_first(const SgAdjPassArgs<T> &pa, int64_t outer, cudaStream_t st)
-{
-    constexpr int V = sizeof(T) == 4 ? 4 : 2;
-    dim3 grid((unsigned)((pa.inner + 128 * V - 1) / (128 * V)), 1, (unsigned)outer);
-    sg_adj_march_j1_kernel<T, P, V, 24, 4><<<grid, 128, 0, st>>>(pa);
-    g_sg_launches.fetch_add(1);
-}
-
-template <typename T>
-static int sg_run_fused(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &ss, SgAdjointHeader *hdr, const T *eval,
-                        const SgFusedPlan &fp, char *ws, cudaStream_t st)
-{
-    const int D = a.nin;
-    SgAdjPassArgs<T> pa{};
-    T *Y = reinterpret_cast<T *>(ws + fp.y_off);
-    pa.X = eval; pa.Y = Y; pa.table = a.table[D - 1]; pa.index = a.index[D - 1]; pa.span_start = ss.start[D - 1];
-    pa.hdr = hdr; pa.inner = a.n_total / a.n_samples[D - 1]; pa.n_d = a.n_samples[D - 1]; pa.c_d = a.n_cp[D - 1];
-    pa.G = (int)(a.n_cp[D - 1] - a.degree[D - 1]); pa.nchunks = 1; pa.path = SG_PATH_FUSED; pa.dim = D - 1; pa.last_dim = -1;
-    pa.table1 = a.table[0]; pa.index1 = a.index[0]; pa.c1 = a.n_cp[0]; pa.n1 = a.n_samples[0]; pa.P1 = a.degree[0];
-    pa.tile_lo = ss.tile_lo; pa.tile_ni = ss.tile_ni; pa.n_tiles = fp.n_tiles; pa.n_slots = fp.n_slots; pa.span_start1 = ss.start[0];
-    switch (a.degree[D - 1]) {
-        case 1: sg_launch_fused_first<T, 1>(pa, a.nout, st); break;
-        case 2: sg_launch_fused_first<T, 2>(pa, a.nout, st); break;
-        default: sg_launch_fused_first<T, 3>(pa, a.nout, st); break;
-    }
-    const T *X = Y;
-    for (int k = 0; k < fp.npassA; ++k) {
-        const SgAdjPass &ps = fp.pass[k];
-        T *out = reinterpret_cast<T *>(ws + ps.out_off);
-        T *part = ps.nchunks > 1 ? reinterpret_cast<T *>(ws + ps.part_off) : out;
-        SgAdjPassArgs<T> pm{};
-        pm.X = X; pm.Y = part; pm.table = a.table[ps.d]; pm.index = a.index[ps.d]; pm.span_start = ss.start[ps.d];
-        pm.hdr = hdr; pm.inner = ps.inner; pm.n_d = ps.n_d; pm.c_d = ps.c_d; pm.G = ps.G; pm.nchunks = ps.nchunks;
-        pm.path = SG_PATH_FUSED; pm.dim = ps.d; pm.last_dim = -1; pm.tile_ni = ss.tile_ni; pm.n_tiles = fp.n_tiles; pm.n_slots = fp.n_slots;
-        sg_run_pass_a<T>(ps, pm, out, part, false, SG_PATH_FUSED, hdr, st);
-        X = out;
-    }
-    const int64_t rest = a.cp_total / a.n_cp[0] * a.nout;
-    const unsigned gy = (unsigned)std::min<int64_t>(rest, 32768);
-    dim3 tgrid(sg_blocks(a.n_cp[0], 128), gy, (unsigned)((rest + gy - 1) / gy));
-    sg_adj_tile_combine_kernel<T><<<tgrid, 128, 0, st>>>(cp, X, ss.tile_lo, ss.tile_ni, fp.n_tiles, fp.n_slots, a.n_cp[0], rest, hdr, SG_PATH_FUSED);
-    g_sg_launches.fetch_add(1);
-    return SG_OK;
+    return std::max(a, mp.ok ? mp.bytes : (size_t)0);
 }
 
 // benchmark hook (include/splinegrids_b200.h): CUDA events around the dominant kernel
@@ -641,23 +378,11 @@ int sg_evaluate_adjoint_fast(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T
     if (!sg_adjoint_fast_supported(a.nin, a.degree, rational)) return SG_ERR_UNSUPPORTED;
     if (g_sg_policy != 2 && a.n_total < 32768) return SG_ERR_UNSUPPORTED;
     char *ws = static_cast<char *>(scratch);
-    SgMarch3Plan m3 = sg_adjoint_march3_plan(a.nin, a.n_samples, a.n_cp, a.nout, a.degree, (int)sizeof(T), rational);
-    if (m3.ok && reinterpret_cast<uintptr_t>(eval) % 16 != 0) m3.ok = false;
-    // zero fill (src/adjoint.jl:61): needed only if the prep kernel flags non-monotone spans (scatter path); the
-    // single-pass pipeline's combine kernel does it itself
-    SgFusedPlan fp = sg_adjoint_fused_plan(a.nin, a.n_samples, a.n_cp, a.nout, a.degree, (int)sizeof(T), rational);
-    if (fp.ok && reinterpret_cast<uintptr_t>(eval) % 16 != 0) fp.ok = false;
+    // zero fill (src/adjoint.jl:61): the double march's post kernel writes every control point itself
     const SgMarch2Plan mp = sg_adjoint_march2_plan(a.nin, a.n_samples, a.n_cp, a.nout, a.degree, (int)sizeof(T), rational);
-    const bool self_zero = m3.ok || (!fp.ok && mp.ok);   // the last kernel writes every cp
-    if (!self_zero) SG_CUDA(cudaMemsetAsync(cp, 0, (size_t)a.cp_total * a.nout * sizeof(T), st));
+    if (!mp.ok) SG_CUDA(cudaMemsetAsync(cp, 0, (size_t)a.cp_total * a.nout * sizeof(T), st));
     int rc;
-    if (m3.ok) {
-        rc = sg_run_march3<T>(cp, a, ss, hdr, eval, m3, ws, st);
-        g_sg_last_variant = "adjoint_march3";
-    } else if (fp.ok) {
-        rc = sg_run_fused<T>(cp, a, ss, hdr, eval, fp, ws, st);
-        g_sg_last_variant = "adjoint_fused_j1";
-    } else if (mp.ok) {
+    if (mp.ok) {
         rc = sg_run_march2<T>(cp, a, ss, hdr, eval, mp, ws, st);
         g_sg_last_variant = "adjoint_march2";
     } else {

@@ -23,10 +23,9 @@
 
 #define SG_ADJ_PIECE 64   // marching steps staged in shared memory at a time
 
-// Which adjoint pipeline a kernel belongs to.  Both pipelines are enqueued when the fused one is eligible on
-// the host side; the device-side flags written by the prep kernel decide which one does the work (the
-// kernels of the other return at their first instruction) -- no host synchronisation.
-enum { SG_PATH_MULTIPASS = 0, SG_PATH_FUSED = 1, SG_PATH_MULTIPASS_FALLBACK = 2 };
+// All fast kernels return at their first instruction when the prep kernel flagged non-monotone span indices (the atomic
+// scatter kernel then does the work) -- no host synchronisation.
+enum { SG_PATH_MULTIPASS = 0 };
 __device__ __forceinline__ bool sg_adj_path_active(const SgAdjointHeader *h, int path)
 {
     (void)path;
@@ -64,16 +63,6 @@ struct SgAdjPassArgs {
     int last_dim;               // -1: no skipping
     int last_P;
     int64_t last_div, last_c;
-    // passes that follow the fused first pass: the contiguous axis is [n_slots][n_tiles]; slots >= tile_ni[tile]
-    // were never written and are skipped
-    const int32_t *tile_ni;
-    int n_tiles;
-    int n_slots;
-    // fused first pass only
-    const int32_t *tile_lo;
-    const int32_t *span_start1;
-    int64_t n1;
-    int P1;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -115,8 +104,6 @@ __global__ void __launch_bounds__(128) sg_adj_march_kernel(const __grid_constant
     if (s_lo >= s_hi) return;                                          // block-uniform
     const int64_t j_lo = a.span_start[s_lo], j_hi = a.span_start[s_hi];
     bool active = q0 < a.inner;
-    if (a.tile_ni != nullptr && active)   // slot axis after the fused first pass: skip never-written slots
-        active = (int)(q0 % a.n_slots) < a.tile_ni[(q0 / a.n_slots) % a.n_tiles];
     const int rows = a.G + P;
     const int64_t inner = a.inner;
 
@@ -447,246 +434,6 @@ __global__ void __launch_bounds__(128) sg_adj_first_dim_rows_kernel(T *__restric
         const int64_t lin = i0 + c1 * r;
         cp[lin] = RATIONAL ? a0 * sg_ldg(weights + lin % cp_total) : a0;
     }
-}
-
-// =============================================================================================
-// FUSED first pass: march along the slowest axis AND contract dimension 1 inside the warp.
-//
-// Same marching structure as sg_adj_march_kernel (thread = V consecutive samples of dimension 1, P+1 live
-// rows in registers).  A warp owns one tile of TS = 32*V consecutive samples of dimension 1.  Completed rows
-// of the marching axis are parked in a warp-private, bank-skewed shared buffer; every NB rows the warp
-// contracts them over dimension 1: lane l gathers control index (tile_lo + l) with its <= RMAX basis weights
-// held in registers (they depend only on the lane) for all NB rows at once (NB independent FMA chains).
-// The pass output therefore shrinks from n_1 to the touched control indices (19 per 64 samples in C3) BEFORE
-// it reaches HBM: C3 writes 80 MB instead of 268 MB and every later pass works on the small array.
-// Only warp-level synchronisation.  Ranges longer than RMAX (many samples per span: emits are rare there) and
-// slots beyond lane 31 (very short spans) use table look-ups instead of register weights: always correct.
-// Layout of Y: [n_slots][n_tiles][M][rows][outer], n_slots = TS + 8, M = product of the middle sample dims.
-// Preconditions (host): n_1 % TS == 0, 16-byte aligned input, one chunk.
-// =============================================================================================
-template <typename T, int P, int V, int RMAX, int NB>
-__global__ void __launch_bounds__(128) sg_adj_march_j1_kernel(const __grid_constant__ SgAdjPassArgs<T> a)
-{
-    if (!sg_adj_path_active(a.hdr, a.path)) return;
-    constexpr int TS = 32 * V;                       // samples of dimension 1 per warp tile
-    constexpr int WB = TS + TS / 4 + 4;              // skewed row length
-    __shared__ __align__(16) T bs[SG_ADJ_PIECE * (P + 1)];
-    __shared__ int ss[SG_ADJ_PIECE];
-    __shared__ T wbuf[4][NB][WB];
-    constexpr int U = 8;
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t q0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;   // inner = n1 * M, always a full tile
-    const int64_t r = blockIdx.z;
-    const int s_lo = P + 1;
-    const int s_hi = (int)a.c_d + 1;
-    const int64_t j_lo = a.span_start[s_lo], j_hi = a.span_start[s_hi];
-    const int64_t inner = a.inner;
-    const bool active = q0 < inner;                   // warp-uniform (inner % TS == 0)
-    const int rows = (int)a.c_d;
-
-    const int64_t qw = q0 - (int64_t)lane * V;        // first sample of the warp tile
-    const int64_t m = qw / a.n1;                      // index over the middle dimensions
-    const int tile = (int)((qw % a.n1) / TS);
-    const int64_t tile_j0 = (int64_t)tile * TS;
-    const int P1 = a.P1;
-
-    // sample range (within the tile) that touches control slot `slot` of this tile
-    auto slot_range = [&](int slot, int64_t &i, int64_t &lo, int &len) {
-        i = (int64_t)a.tile_lo[tile] + slot + 1;      // 1-based control index
-        const int64_t s0 = i > P1 + 1 ? i : P1 + 1;
-        const int64_t s1 = i + P1 < a.c1 ? i + P1 : a.c1;
-        lo = max((int64_t)a.span_start1[s0], tile_j0);
-        const int64_t hi = min((int64_t)a.span_start1[s1 + 1], tile_j0 + TS);
-        len = (int)max((int64_t)0, hi - lo);
-    };
-
-    int ni = 0, len = 0, rel = 0;
-    T w[RMAX];
-#pragma unroll
-    for (int t = 0; t < RMAX; ++t) w[t] = T(0);
-    if (active) {
-        ni = a.tile_ni[tile];
-        if (lane < ni) {
-            int64_t i, lo;
-            slot_range(lane, i, lo, len);
-            rel = (int)(lo - tile_j0);
-#pragma unroll
-            for (int t = 0; t < RMAX; ++t) {
-                if (t < len) {
-                    const int64_t j = lo + t;
-                    const int k = (int)(i - sg_ldg(a.index1 + j) + P1);
-                    w[t] = sg_ldg(a.table1 + j + a.n1 * k);
-                } else {
-                    w[t] = T(0);
-                }
-            }
-        }
-    }
-    // warp-uniform: every lane's range fits the register weights and the tile needs no more than 32 slots
-    const bool fast_gather = __all_sync(0xffffffffu, len <= RMAX && ni <= 32);
-    const int maxlen = __reduce_max_sync(0xffffffffu, len);    // lanes without a slot have len 0 and zero weights
-    rel = min(rel, TS - 1);
-
-    const T *__restrict__ xp = a.X + q0 + inner * (j_lo + a.n_d * r);
-    // Y index = slot + n_slots*(tile + n_tiles*(m + M*(row + rows*r)))
-    const int64_t M = inner / a.n1;
-    const int64_t y_row = (int64_t)a.n_slots * a.n_tiles * M;
-    T *__restrict__ yp = a.Y + (int64_t)a.n_slots * (tile + (int64_t)a.n_tiles * m) + y_row * ((int64_t)rows * r);
-
-    T acc[V][P + 1];
-#pragma unroll
-    for (int v = 0; v < V; ++v)
-#pragma unroll
-        for (int k = 0; k <= P; ++k) acc[v][k] = T(0);
-    int cur = s_lo;
-    int nb = 0;                                       // rows parked in the warp buffer
-    T(*__restrict__ wb)[WB] = wbuf[warp];
-
-    // contract the nb parked rows over dimension 1 and write them
-    auto flush_rows = [&]() {
-        __syncwarp();
-        if (fast_gather) {
-            // branch-free over the lanes: padded weights are zero, indices are clamped to the tile
-            T sum[NB];
-#pragma unroll
-            for (int q = 0; q < NB; ++q) sum[q] = T(0);
-#pragma unroll
-            for (int t = 0; t < RMAX; ++t) {
-                if (t < maxlen) {   // warp-uniform
-                    const int j = min(rel + t, TS - 1);
-                    const int js = j + (j >> 2);
-#pragma unroll
-                    for (int q = 0; q < NB; ++q) sum[q] = fma(w[t], wb[q][js], sum[q]);
-                }
-            }
-            if (lane < ni) {
-#pragma unroll
-                for (int q = 0; q < NB; ++q)
-                    if (q < nb) yp[lane + y_row * q] = sum[q];
-            }
-        } else {   // general: any number of slots, any range length
-            for (int slot = lane; slot < ni; slot += 32) {
-                int64_t i, lo;
-                int ln;
-                slot_range(slot, i, lo, ln);
-                const int rl = (int)(lo - tile_j0);
-                for (int q = 0; q < nb; ++q) {
-                    T sum = T(0);
-                    for (int t = 0; t < ln; ++t) {
-                        const int64_t jg = lo + t;
-                        const int k = (int)(i - sg_ldg(a.index1 + jg) + P1);
-                        const int j = rl + t;
-                        sum = fma(sg_ldg(a.table1 + jg + a.n1 * k), wb[q][j + (j >> 2)], sum);
-                    }
-                    yp[slot + y_row * q] = sum;
-                }
-            }
-        }
-        yp += y_row * nb;
-        nb = 0;
-        __syncwarp();
-    };
-
-    auto park_row = [&](const T (&o)[V]) {   // o = this thread's V completed values of one row
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-            const int j = lane * V + v;
-            wb[nb][j + (j >> 2)] = o[v];
-        }
-        if (++nb == NB) flush_rows();
-    };
-
-    auto emit_oldest = [&]() {
-        T o[V];
-#pragma unroll
-        for (int v = 0; v < V; ++v) o[v] = acc[v][0];
-        park_row(o);
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-#pragma unroll
-            for (int k = 0; k < P; ++k) acc[v][k] = acc[v][k + 1];
-            acc[v][P] = T(0);
-        }
-        ++cur;
-    };
-
-    auto step = [&](int s, const T (&x)[V]) {
-        const int sp = ss[s];
-        if (cur < sp) {
-            do emit_oldest(); while (cur < sp);
-        }
-        T b[P + 1];
-#pragma unroll
-        for (int k = 0; k <= P; ++k) b[k] = bs[s * (P + 1) + k];
-#pragma unroll
-        for (int k = 0; k <= P; ++k)
-#pragma unroll
-            for (int v = 0; v < V; ++v) acc[v][k] = fma(b[k], x[v], acc[v][k]);
-    };
-
-    for (int64_t jp = j_lo; jp < j_hi; jp += SG_ADJ_PIECE) {
-        const int np = (int)min((int64_t)SG_ADJ_PIECE, j_hi - jp);
-        __syncthreads();
-        for (int s = threadIdx.x; s < np; s += blockDim.x) {
-            ss[s] = sg_ldg(a.index + jp + s);
-#pragma unroll
-            for (int k = 0; k <= P; ++k) bs[s * (P + 1) + k] = sg_ldg(a.table + jp + s + a.n_d * k);
-        }
-        __syncthreads();
-        if (!active) continue;
-        int s = 0;
-        for (; s + U <= np; s += U) {
-            T xs[U][V];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                sg_load_vec<T, V>(xp, xs[u]);
-                xp += inner;
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) step(s + u, xs[u]);
-        }
-        for (; s < np; ++s) {
-            T x1[V];
-            sg_load_vec<T, V>(xp, x1);
-            xp += inner;
-            step(s, x1);
-        }
-    }
-    if (!active) return;
-    while (cur < s_hi) emit_oldest();
-#pragma unroll
-    for (int k = 0; k < P; ++k) {
-        T o[V];
-#pragma unroll
-        for (int v = 0; v < V; ++v) o[v] = acc[v][k];
-        park_row(o);
-    }
-    if (nb > 0) flush_rows();
-}
-
-// Final step of the fused pipeline: add the (<= few) warp tiles that share a control index of dimension 1.
-// Z: [n_slots][n_tiles][rest], cp: [c1][rest].  grid = (ceil(c1/128), rest split over y and z).
-template <typename T>
-__global__ void __launch_bounds__(128) sg_adj_tile_combine_kernel(T *__restrict__ cp, const T *__restrict__ Z, const int32_t *__restrict__ tile_lo,
-                                                                  const int32_t *__restrict__ tile_ni, int n_tiles, int n_slots, int64_t c1,
-                                                                  int64_t rest, const SgAdjointHeader *hdr, int path)
-{
-    if (!sg_adj_path_active(hdr, path)) return;
-    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // 0-based control index
-    const int64_t r = (int64_t)blockIdx.y + (int64_t)gridDim.y * blockIdx.z;
-    if (i0 >= c1 || r >= rest) return;
-    // first tile with tile_lo + tile_ni > i0 (tile_lo and tile_lo+tile_ni are non-decreasing)
-    int lo = 0, hi = n_tiles;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (tile_lo[mid] + tile_ni[mid] > i0) hi = mid; else lo = mid + 1;
-    }
-    T acc = T(0);
-    const T *__restrict__ zr = Z + (int64_t)n_slots * n_tiles * r;
-    for (int t = lo; t < n_tiles && tile_lo[t] <= i0; ++t)
-        if (i0 < tile_lo[t] + tile_ni[t]) acc += sg_ldg(zr + (i0 - tile_lo[t]) + (int64_t)n_slots * t);
-    cp[i0 + c1 * r] = acc;
 }
 
 // =============================================================================================

@@ -160,11 +160,11 @@ CASES = [
     ((16, 16, 16), (3, 3, 3), (40, 36, 44), 1, "Float64", 0, False),
     ((16, 16), (3, 3), (128, 96), 3, "Float32", 0, True),
     ((20, 3), (2, 2), (3, 50), 2, "Float64", 0, False),                   # fewer samples than spans
-    # shapes eligible for the fused adjoint (n_1 multiple of the 32-lane tile, enough columns)
+    # 3-D / 4-D shapes with n_1 a multiple of 64
     ((20, 11, 9), (3, 3, 3), (128, 400, 20), 1, "Float64", 0, False),
     ((40, 9, 7), (2, 3, 2), (256, 400, 12), 2, "Float32", 1, False),
     ((100, 8, 6), (2, 2, 2), (128, 400, 20), 1, "Float64", 0, False),     # > 32 control indices per tile: device-side fallback
-    ((12, 6, 9, 5), (3, 2, 3, 1), (64, 20, 40, 5), 2, "Float64", 0, False),   # Nin = 4 through the fused pipeline
+    ((12, 6, 9, 5), (3, 2, 3, 1), (64, 20, 40, 5), 2, "Float64", 0, False),   # Nin = 4
 ]
 
 
@@ -198,24 +198,16 @@ def test_evaluate_and_adjoint_vs_oracle(S, case, policy):
         S.set_kernel_policy(0)
 
 
-FUSED_CASES = [c for c in CASES if c[2][0] % 64 == 0 and len(c[0]) >= 3]
-
-
 MARCH2_CASES = [((20, 11, 9), (3, 3, 3), (128, 400, 20), 1, "Float64", 0, False),
                 ((100, 8, 6), (2, 2, 2), (128, 400, 20), 1, "Float64", 0, False),
                 ((30, 12, 25), (2, 1, 1), (256, 40, 300), 2, "Float32", 0, False),
                 ((9, 40, 7), (3, 3, 3), (130, 45, 33), 1, "Float64", 0, False)]      # ~1 sample per span in dim 2, ragged n1
 
 
-@pytest.mark.parametrize("case,env,variant",
-                         [(c, "SG_ADJ_FUSED", "adjoint_fused_j1") for c in FUSED_CASES] +
-                         [(c, "SG_ADJ_MARCH2", "adjoint_march2") for c in MARCH2_CASES],
-                         ids=[f"fused-{c[0]}-{c[1]}" for c in FUSED_CASES] + [f"march2-{c[0]}-{c[1]}" for c in MARCH2_CASES])
-def test_optin_adjoint_pipelines_vs_oracle(S, case, env, variant, monkeypatch):
-    """The opt-in experimental adjoint pipelines against the C oracle:
-    SG_ADJ_FUSED=1  -- march along the slowest axis + warp-level contraction of dimension 1 (incl. tiles with
-                       more than 32 control indices);
-    SG_ADJ_MARCH2=1 -- 3-D register-resident double march over dimensions 3 and 2."""
+@pytest.mark.parametrize("case,env,variant", [(c, "SG_ADJ_MARCH2", "adjoint_march2") for c in MARCH2_CASES],
+                         ids=[f"march2-{c[0]}-{c[1]}" for c in MARCH2_CASES])
+def test_forced_double_march_vs_oracle(S, case, env, variant, monkeypatch):
+    """SG_ADJ_MARCH2=1 forces the 3-D double march over dimensions 3 and 2 on small shapes; against the C oracle."""
     from gpu_helpers import make_grid, oracle_adjoint
     n_cp, deg, n_s, nout, ft, mdo, nurbs = case
     grid, cp, w, rng = make_grid(n_cp, deg, n_s, nout, ft, mdo=0, seed=21)
@@ -250,7 +242,6 @@ def test_double_march_post_kernel_vs_oracle(S, case, distribution, monkeypatch):
     e = np.asfortranarray(rng.random(tuple(n_s) + (nout,)).astype(cp.dtype))
     g = torch.full_like(grid.control_points.obtain(), -7.0)
     monkeypatch.setenv("SG_ADJ_MARCH2", "1")
-    monkeypatch.setenv("SG_ADJ_MARCH3", "0")
     S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g)
     assert S.last_variant() == "adjoint_march2"
     gref = oracle_adjoint(grid, e)
@@ -266,75 +257,6 @@ def test_double_march_post_kernel_vs_oracle(S, case, distribution, monkeypatch):
         g3 = torch.full_like(g, 1.0)
         S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g3)
         assert rel_err(S.to_numpy(g3), gref) <= _tol(ft), ctas
-
-
-MARCH3_CASES = [
-    # n_cp, degree, n_samples, nout, float type, extra environment
-    ((20, 11, 9), (3, 3, 3), (128, 400, 20), 1, "Float64", {}),
-    ((100, 8, 6), (2, 2, 2), (128, 400, 20), 1, "Float64", {}),                 # > 40 control indices per column block
-    ((30, 12, 25), (2, 1, 1), (256, 40, 300), 2, "Float32", {}),
-    ((9, 40, 7), (3, 3, 3), (130, 45, 33), 1, "Float64", {}),                   # ~1 sample per span in dim 2, ragged n1
-    ((16, 16, 16), (3, 3, 3), (40, 36, 44), 1, "Float64", {}),
-    ((40, 20, 24), (3, 2, 2), (300, 90, 100), 3, "Float64", {}),                # mixed degree in dim 1, Nout 3
-    ((12, 7, 30), (5, 3, 3), (512, 64, 70), 1, "Float64", {}),                  # degree 5 in dim 1 (table look-ups), 4 passes
-    ((33, 9, 35), (3, 3, 3), (136, 140, 150), 1, "Float64", {}),                # ~23 rows per span in dim 2: 5 passes
-    ((33, 34, 35), (3, 3, 3), (136, 140, 150), 2, "Float64", {"SG_ADJ_M3_W": "7"}),     # few workers: long segments
-    ((33, 34, 35), (3, 3, 3), (136, 140, 150), 1, "Float64", {"SG_ADJ_M3_W": "1500"}),  # many workers: 1-2 planes each
-    ((33, 34, 35), (1, 1, 1), (136, 140, 150), 1, "Float32", {"SG_ADJ_M3_W": "97"}),
-    ((20, 30, 9), (2, 2, 2), (128, 25, 200), 1, "Float64", {}),                 # fewer samples than spans in dim 2
-]
-
-
-@pytest.mark.parametrize("distribution", ["equispaced", "random"])
-@pytest.mark.parametrize("case", MARCH3_CASES, ids=[f"{c[0]}-{c[1]}-{c[4]}-{'-'.join(c[5].values())}" for c in MARCH3_CASES])
-def test_single_pass_3d_adjoint_vs_oracle(S, case, distribution, monkeypatch):
-    """The single-pass 3-D adjoint (sg_adjoint_march3.cuh: TMA-fed ring, all three contractions inside the CTA,
-    persistent workers on a linear partition, halo combine) against the C oracle."""
-    from gpu_helpers import make_grid, oracle_adjoint
-    n_cp, deg, n_s, nout, ft, env = case
-    grid, cp, w, rng = make_grid(n_cp, deg, n_s, nout, ft, mdo=0, seed=31, distribution=distribution)
-    e = np.asfortranarray(rng.random(tuple(n_s) + (nout,)).astype(cp.dtype))
-    g = torch.full_like(grid.control_points.obtain(), -3.0)
-    monkeypatch.setenv("SG_ADJ_MARCH3", "1")
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
-    S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g)
-    assert S.last_variant() == "adjoint_march3"
-    gref = oracle_adjoint(grid, e)
-    assert rel_err(S.to_numpy(g), gref) <= _tol(ft)
-    assert max_rel_err(S.to_numpy(g), gref) <= 10 * _tol(ft)
-    if distribution == "equispaced":
-        # deterministic (no atomics; the scatter fallback is not taken for evenly spread samples): same bits again
-        g2 = torch.full_like(g, 9.0)
-        S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g2)
-        assert torch.equal(g, g2)
-
-
-def test_single_pass_3d_adjoint_clustered_samples_fall_back_on_device(S, monkeypatch):
-    """All samples of dimension 2 inside one knot-span tile: that (block, tile) column would need more segments than
-    the partial buffer reserves, the kernel raises the header flag and the atomic scatter takes over (no host sync)."""
-    from gpu_helpers import O
-    rng = np.random.default_rng(6)
-    n_cp, deg, n_s = (12, 40, 10), (2, 2, 2), (128, 64, 48)
-    dims, odims = [], []
-    for d, (c, p, n) in enumerate(zip(n_cp, deg, n_s)):
-        kv = S.KnotVector.clamped(c, p, float_type_="Float64")
-        sp = np.sort(rng.random(n)) * (0.05 if d == 1 else 1.0)      # dim 2: everything in the first two spans
-        sd = S.SplineDimension.from_fields(p, 0, kv, S.to_device(sp), torch.zeros(n, dtype=torch.int32, device="cuda"),
-                                           S.jl_zeros((n, p + 1, 1), torch.float64, "cuda"))
-        S.build_(sd)
-        idx = O.span_indices(sp, S.to_numpy(kv.knots_all), p)
-        odims.append((O.basis_tables(S.to_numpy(kv.knots_all), sp, idx, p, 0), idx))
-        dims.append(sd)
-    grid = S.SplineGrid(tuple(dims), 1)
-    e = np.asfortranarray(rng.random(n_s + (1,)))
-    monkeypatch.setenv("SG_ADJ_MARCH3", "1")
-    monkeypatch.setenv("SG_ADJ_M3_W", "400")
-    g = torch.full_like(grid.control_points.obtain(), 4.0)
-    S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g)
-    assert S.last_variant() == "adjoint_march3"
-    gref = O.evaluate_adjoint([t for t, _ in odims], [i for _, i in odims], list(deg), [0, 0, 0], e, n_cp + (1,))
-    assert rel_err(S.to_numpy(g), gref) <= 1e-12
 
 
 def test_evaluate_with_raw_and_reshaped_arrays(S):
