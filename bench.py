@@ -66,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "25", "-i", str(self.gpu_index)],
+                                          "-lms", "10", "-i", str(self.gpu_index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -157,15 +157,38 @@ def cpu_reference_setup(planes: int):
     return step, values, OC.max_threads()
 
 
-def run_cpu_reference(steps: int, warmup: int, planes: int):
+try:
+    _AFFINITY0 = set(os.sched_getaffinity(0))       # before any NUMA binding of the GPU arm
+except AttributeError:
+    _AFFINITY0 = set(range(os.cpu_count() or 1))
+
+
+def host_cores() -> int:
+    """Host threads this process may use (the CPU affinity mask at start-up; torchrun exports OMP_NUM_THREADS=1,
+    which is a default for ITS workers, not a limit of the box)."""
+    return max(1, len(_AFFINITY0))
+
+
+def run_cpu_reference(steps: int, warmup: int, planes: int, budget_s: float = None):
+    """Times `steps` steps (fewer if they would not fit `budget_s` seconds; the number run is returned)."""
+    from oracle import oracle_c as OC
+    try:
+        os.sched_setaffinity(0, _AFFINITY0)         # undo the GPU arm's NUMA binding: the CPU arm uses the whole box
+    except (AttributeError, OSError):
+        pass
+    OC.set_threads(host_cores())                    # regardless of an inherited OMP_NUM_THREADS
     step, values, cores = cpu_reference_setup(planes)
-    for _ in range(warmup):
+    t0 = time.perf_counter()
+    for _ in range(max(1, warmup)):
         step()
+    dt_est = (time.perf_counter() - t0) / max(1, warmup)
+    if budget_s is not None:
+        steps = max(1, min(steps, int(budget_s / max(dt_est, 1e-9))))
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    return values / dt, dt, cores
+    return values / dt, dt, cores, steps
 
 
 def main_reference(args):
@@ -173,8 +196,9 @@ def main_reference(args):
     if rank != 0:
         return 0
     planes = args.cpu_planes
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-    value, dt, cores = run_cpu_reference(steps, warmup, planes)
+    warmup = max(1, args.warmup)
+    # as many of the requested steps as fit ~150 s of CPU time (one step of the 32-plane sample takes ~0.5 s)
+    value, dt, cores, steps = run_cpu_reference(args.steps, warmup, planes, budget_s=150.0)
     sample = (f"slab of {planes}/512 planes of the C3 grid (512x512x{planes} samples, all 128^3 control points), "
               f"evaluate!+adjoint, C/OpenMP restatement of the reference algorithm (Julia unavailable), {cores} threads")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
@@ -191,6 +215,69 @@ def main_reference(args):
 # --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
+
+
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pin this process (and therefore its pinned host buffers, first touch) to the NUMA node of its GPU: eight ranks
+    whose staging buffers sit on the wrong socket share the inter-socket link.  Best effort; returns the node or None."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local_rank), "pci_device_id", 0)
+        path = Path(f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node")
+        node = int(path.read_text().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = set(os.sched_getaffinity(0)) & set(cpus)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
+def check_exchange(S, sh, grid, e_in, grad, rank, world, dev):
+    """N > 1 parity gate, always on: (1) the exchanged gradient against an NCCL all-reduce of the local partial
+    gradients; (2) on rank 0, control planes 4..6 of the exchanged gradient against the C oracle's adjoint (the
+    reference's algorithm, src/adjoint.jl:11-39) of the first 32 sample planes (those planes see no other sample)."""
+    import torch
+    import torch.distributed as dist
+    S.evaluate_adjoint_(grid, eval=e_in, control_points=grad)
+    ref = grad.clone()
+    S.allreduce_gradient_(ref)
+    grad.fill_(float("nan"))
+    sh.evaluate_adjoint_(eval=e_in, control_points=grad)
+    torch.cuda.synchronize()
+    err = float((grad - ref).norm() / ref.norm())
+    out = {"kind": sh.exchange_kind, "rel_err_vs_allreduce": err}
+    if sh.exchange is not None:
+        ep, timed_out = sh.exchange.status()
+        out["exchanges_completed"], out["timed_out"] = ep, timed_out
+    if rank == 0:
+        from oracle import oracle_c as OC
+        OC.set_threads(host_cores())
+        w = WORKLOAD
+        n_pl = 32
+        assert grid.eval.shape[2] >= n_pl
+        tabs = [np.asfortranarray(S.to_numpy(sd.eval)) for sd in grid.spline_dimensions]
+        idxs = [np.ascontiguousarray(S.to_numpy(sd.sample_indices)) for sd in grid.spline_dimensions]
+        tabs[2], idxs[2] = np.asfortranarray(tabs[2][:n_pl]), np.ascontiguousarray(idxs[2][:n_pl])
+        assert int(idxs[2][-1]) > 6 + 4                      # spans up to 10 (1-based) lie completely inside the sample
+        e_np = np.asfortranarray(S.to_numpy(e_in[:, :, :n_pl, :]))
+        gref = OC.evaluate_adjoint(tabs, idxs, list(w["degree"]), [0, 0, 0], e_np, tuple(w["n_cp"]) + (w["nout"],))
+        got = S.to_numpy(grad)[:, :, 4:7, :]
+        out["rel_err_vs_oracle_planes_4_6"] = float(np.linalg.norm(got - gref[:, :, 4:7, :]) / np.linalg.norm(gref[:, :, 4:7, :]))
+    flag = torch.tensor([0 if (err <= 1e-12 and out.get("rel_err_vs_oracle_planes_4_6", 0.0) <= 1e-12
+                               and not out.get("timed_out", False)) else 1], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    out["ok"] = int(flag.item()) == 0
+    return out
 
 
 def main_gpu(args):
@@ -210,8 +297,10 @@ def main_gpu(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    world_env = world
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world_env > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -246,16 +335,13 @@ def main_gpu(args):
 
     values_per_step = 2 * int(np.prod(w["n_samples"])) * w["nout"]      # whole job, both ops
     exchange_check = None
-    if world > 1 and args.check:
-        # the exchanged gradient must equal the all-reduced local partial gradients
-        S.evaluate_adjoint_(grid, eval=e_in, control_points=grad)
-        ref = grad.clone()
-        S.allreduce_gradient_(ref)
-        sh.evaluate_adjoint_(eval=e_in, control_points=grad)
-        torch.cuda.synchronize()
-        err = float((grad - ref).norm() / ref.norm())
-        exchange_check = {"kind": sh.exchange_kind, "rel_err_vs_allreduce": err}
-        assert err < 1e-12, f"gradient exchange mismatch: {err}"
+    if world > 1:
+        exchange_check = check_exchange(S, sh, grid, e_in, grad, rank, world, dev)
+        if not exchange_check["ok"]:
+            if rank == 0:
+                print(f"[bench] gradient exchange FAILED its parity gate: {exchange_check}", file=sys.stderr)
+            dist.destroy_process_group()
+            return 3
 
     # ---- kernel-only timing: K steps between two events, max over ranks ---------------------------
     for _ in range(args.warmup):
@@ -264,9 +350,9 @@ def main_gpu(args):
     # The step is captured once in a CUDA graph (two steps per replay: the peer-memory exchange alternates between two
     # staging buffers) and replayed: the same kernels, without the per-call host cost that bounds thin slabs.
     cap, cap_err = None, None
-    # N > 1: eager by default -- capturing the symmetric-memory barrier / NCCL all-reduce in a graph hung (barrier) or
-    # blocked the process-group teardown (NCCL) when tried at N = 2; `--graph` forces the attempt.
-    if (world == 1 and not args.no_graph) or args.graph:
+    # N > 1: the peer-memory exchange is plain kernels with a device-side flag barrier, so the step is captured as well;
+    # with the NCCL all-reduce (--nccl-allreduce) the step launches eagerly unless --graph forces the attempt.
+    if (not args.no_graph and (world == 1 or sh.exchange is not None)) or args.graph:
         try:
             cap = S.CapturedCalls(step, unroll=2, warmup=1)
             for _ in range(2):
@@ -440,13 +526,13 @@ def main_gpu(args):
     e2e = {"value": values_per_step / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": e2e_steps,
            "h2d_bytes_per_step": int((cp.numel() + e_in.numel()) * elem),
            "d2h_bytes_per_step": int((grid.eval.numel() + cp.numel()) * elem),
-           "note": "per rank; pinned host buffers; uploads, kernels and downloads on three streams (full-duplex PCIe), all "
+           "numa_node": numa_node, "note": "per rank; pinned host buffers (process bound to the GPU's NUMA node); uploads, kernels and downloads on three streams (full-duplex PCIe), all "
                    "copies + kernels + syncs inside the timed region"}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, dts, cores = run_cpu_reference(steps=2, warmup=1, planes=args.cpu_planes)
+        v, dts, cores, _ = run_cpu_reference(steps=8, warmup=1, planes=args.cpu_planes, budget_s=15.0)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step_sample": dts * 1e3,
                "sample": f"slab of {args.cpu_planes}/512 planes of the same grid, evaluate!+adjoint, C/OpenMP restatement "
                          f"of the reference algorithm (Julia not installed, the reference package cannot run)"}
@@ -477,12 +563,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-planes", type=int, default=32, help="slab thickness of the bounded CPU sample")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nccl-allreduce", action="store_true", help="N>1: use the NCCL all-reduce instead of the peer-memory exchange")
     ap.add_argument("--graph", action="store_true", help="N>1: also try to capture the step (with its gradient exchange) in a CUDA graph")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--check", action="store_true", help="N>1: verify the exchanged gradient against an NCCL all-reduce")
+    ap.add_argument("--check", action="store_true", help="(kept for compatibility: the N>1 exchange check always runs)")
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/)")
     args = ap.parse_args()

@@ -199,23 +199,26 @@ int sg_allreduce_sum_f64(double *buf, int64_t count, sg_comm *comm, void *stream
  *                     rank's staging buffer with peer-to-peer stores; peer_stage is a HOST array of `world`
  *                     device pointers (this rank's own buffer included).  Staging layout per rank:
  *                     [world][nout][max_planes][plane_elems].
- * (all ranks then synchronise on the stream -- barrier supplied by the host framework --)
+ * (all ranks then synchronise: sg_exchange_signal + sg_exchange_wait_reduce below, or a host-framework barrier)
  * sg_exchange_reduce: grad[:, k, o] = sum over ranks r whose support covers plane k of stage[r][o][k-k0_r][:],
  *                     summed in rank order (deterministic); k0s / nps are HOST arrays of length world. */
 /* sg_evaluate_adjoint_push: sg_evaluate_adjoint followed by sg_exchange_push of the result, as ONE call.  When the
  * 3-D double-march pipeline runs, its last kernel stores every finished control plane of the support straight into the
  * peers' staging slots (peer-to-peer stores overlapping the computation; no separate push kernel); other pipelines
- * run the push kernel afterwards.  Either way the staging buffers hold what sg_exchange_push would have written. */
+ * run the push kernel afterwards.  Either way the staging buffers hold what sg_exchange_push would have written.
+ * keep_local = 1: `control_points` holds the local partial gradient on return (as after sg_evaluate_adjoint);
+ * keep_local = 0: its contents are unspecified (the caller is about to overwrite it with the reduce; the fused pipeline
+ * then skips its own 16.8 MB of zero / result writes on C3). */
 int sg_evaluate_adjoint_push_f32(float *control_points, int nin, const int64_t *n_samples, const int64_t *n_cp, int nout,
                                  const float *const *tables, const int32_t *const *sample_indices, const int *degree,
                                  const int *max_derivative_order, const int *derivative_order, const float *eval,
                                  const float *weights, void *workspace, size_t workspace_bytes, void *const *peer_stage,
-                                 int world, int my_rank, int64_t k0, int64_t np, int64_t max_planes, void *stream);
+                                 int world, int my_rank, int64_t k0, int64_t np, int64_t max_planes, int keep_local, void *stream);
 int sg_evaluate_adjoint_push_f64(double *control_points, int nin, const int64_t *n_samples, const int64_t *n_cp, int nout,
                                  const double *const *tables, const int32_t *const *sample_indices, const int *degree,
                                  const int *max_derivative_order, const int *derivative_order, const double *eval,
                                  const double *weights, void *workspace, size_t workspace_bytes, void *const *peer_stage,
-                                 int world, int my_rank, int64_t k0, int64_t np, int64_t max_planes, void *stream);
+                                 int world, int my_rank, int64_t k0, int64_t np, int64_t max_planes, int keep_local, void *stream);
 int sg_exchange_push_f32(const float *grad, void *const *peer_stage, int world, int my_rank, int64_t plane_elems,
                          int64_t c_last, int nout, int64_t k0, int64_t np, int64_t max_planes, void *stream);
 int sg_exchange_push_f64(const double *grad, void *const *peer_stage, int world, int my_rank, int64_t plane_elems,
@@ -224,6 +227,30 @@ int sg_exchange_reduce_f32(float *grad, const float *stage, int world, const int
                            int64_t plane_elems, int64_t c_last, int nout, int64_t max_planes, void *stream);
 int sg_exchange_reduce_f64(double *grad, const double *stage, int world, const int64_t *k0s, const int64_t *nps,
                            int64_t plane_elems, int64_t c_last, int nout, int64_t max_planes, void *stream);
+
+
+/* ---- flag-synchronised exchange: the barrier between push and reduce inside the C ABI (no host framework) ----------
+ * flags      peer-mapped array of `world` uint64 per rank, zero-initialised once: flags[r] on rank q counts the exchanges
+ *            whose push from rank r has completely landed in q's staging buffer (monotone, never reset).
+ * local_sync SG_EXCHANGE_SYNC_BYTES of LOCAL device memory, zero-initialised once: the number of exchanges this rank has
+ *            completed lives there, on the device, so the calls can be captured in a CUDA graph and replayed.
+ * sg_exchange_signal       stream-ordered after this rank's push: release-store of (epoch + 1) into flags[my_rank] of every
+ *                          rank (peer_flags: HOST array of `world` device pointers to the ranks' flag arrays).
+ * sg_exchange_wait_reduce  waits ON THE DEVICE until all `world` flags of this rank reached (epoch + 1), then reduces like
+ *                          sg_exchange_reduce and publishes the new epoch.  peer_flags_or_null != NULL: the signal is
+ *                          issued by the same kernel first (one launch for signal + barrier + reduce).
+ * Consecutive exchanges must alternate between TWO staging buffers (they may share flags and local_sync).  All ranks must
+ * have their kernels in flight concurrently (one process or thread per GPU); a peer that never signals makes the wait give
+ * up after 20 s and raises the `timed_out` flag that sg_exchange_status reports (blocking: it synchronises `stream`). */
+#define SG_EXCHANGE_SYNC_BYTES 64
+int sg_exchange_signal(void *const *peer_flags, int world, int my_rank, const void *local_sync, void *stream);
+int sg_exchange_status(const void *local_sync, unsigned long long *epoch, int *timed_out, void *stream);
+int sg_exchange_wait_reduce_f32(float *grad, const float *stage, const void *my_flags, void *local_sync,
+                                void *const *peer_flags_or_null, int world, int my_rank, const int64_t *k0s, const int64_t *nps,
+                                int64_t plane_elems, int64_t c_last, int nout, int64_t max_planes, void *stream);
+int sg_exchange_wait_reduce_f64(double *grad, const double *stage, const void *my_flags, void *local_sync,
+                                void *const *peer_flags_or_null, int world, int my_rank, const int64_t *k0s, const int64_t *nps,
+                                int64_t plane_elems, int64_t c_last, int nout, int64_t max_planes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -55,9 +55,10 @@ __global__ void __launch_bounds__(128, 5) sg_adj_post2_kernel(T *__restrict__ cp
     const int sf = hdr->span_first[2], sl = hdr->span_last[2];
     // This kernel writes EVERY control point (no memset before the pipeline): zeros outside the support of this (slab
     // of the) grid, and zeros everywhere if the prep kernel flagged non-monotone spans (the scatter kernel accumulates).
+    const bool write_local = push.world == 0 || push.keep_local != 0;
     if (!sg_adj_path_active(hdr, path) || i3 < sf - P || i3 > sl) {
         const int64_t iz = ib * 128 + tid;
-        if (iz < c1) {
+        if (iz < c1 && write_local) {
             T *__restrict__ out = cp + iz + c1 * (i2_0 + c2 * ((i3 - 1) + c3 * o));
 #pragma unroll
             for (int q = 0; q < G2; ++q)
@@ -160,10 +161,12 @@ __global__ void __launch_bounds__(128, 5) sg_adj_post2_kernel(T *__restrict__ cp
         }
     }
     if (valid) {
-        T *__restrict__ out = cp + i1 + c1 * (i2_0 + c2 * ((i3 - 1) + c3 * o));
+        if (write_local) {
+            T *__restrict__ out = cp + i1 + c1 * (i2_0 + c2 * ((i3 - 1) + c3 * o));
 #pragma unroll
-        for (int q = 0; q < G2; ++q)
-            if (i2_0 + q < c2) out[c1 * q] = acc[q];
+            for (int q = 0; q < G2; ++q)
+                if (i2_0 + q < c2) out[c1 * q] = acc[q];
+        }
         // Fused gradient push (slab-sharded grids): control plane i3 is plane l = i3 - (sf - P) of this rank's support;
         // it goes into this rank's slot of every rank's staging buffer with peer-to-peer stores (256 contiguous bytes per
         // warp and row), overlapping the rest of the kernel.  sg_exchange_reduce sums the slots after the barrier.

@@ -96,6 +96,8 @@ struct SgPushSpec {
     void *stage[SG_MAX_PEERS];   // staging buffer of every rank (peer-mapped), layout [world][nout][max_planes][plane_elems]
     int world, my_rank;          // world == 0: no push
     long long max_planes;
+    int keep_local;              // 0: the caller does not need the local partial gradient (the reduce overwrites it): the fused
+                                 // pipeline then skips its own writes of the control-point array (zeros and results)
 };
 extern thread_local const SgPushSpec *g_sg_push;   // set around sg_evaluate_adjoint_impl by the push entry point
 extern thread_local bool g_sg_push_done;           // the pipeline that ran did the push itself

@@ -195,13 +195,13 @@ extern "C" int sg_exchange_push_f64(const double *, void *const *, int, int, int
                                                   const int *degree, const int *mdo, const int *der, const T *eval,  \
                                                   const T *weights, void *workspace, size_t workspace_bytes,         \
                                                   void *const *peer_stage, int world, int my_rank, int64_t k0,       \
-                                                  int64_t np, int64_t max_planes, void *stream)                      \
+                                                  int64_t np, int64_t max_planes, int keep_local, void *stream)      \
     {                                                                                                                \
         if (!peer_stage || world < 1 || world > SG_MAX_PEERS || my_rank < 0 || my_rank >= world || nin < 1)          \
             return SG_ERR_INVALID_ARGUMENT;                                                                          \
         SgPushSpec spec{};                                                                                           \
         for (int r = 0; r < world; ++r) spec.stage[r] = peer_stage[r];                                               \
-        spec.world = world; spec.my_rank = my_rank; spec.max_planes = max_planes;                                    \
+        spec.world = world; spec.my_rank = my_rank; spec.max_planes = max_planes; spec.keep_local = keep_local;      \
         g_sg_push = &spec; g_sg_push_done = false;                                                                   \
         int rc = sg_evaluate_adjoint_impl<T>(cp, nin, n_samples, n_cp, nout, tables, indices, degree, mdo, der,      \
                                              eval, weights, workspace, workspace_bytes, stream);                     \

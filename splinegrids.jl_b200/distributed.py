@@ -59,11 +59,13 @@ class PeerGradientExchange:
     """Gradient exchange over NVLink peer memory (replaces the all-reduce).
 
     A slab's partial gradient is non-zero only on the control planes its samples touch.  Every rank pushes
-    those planes into its slot of every peer's staging buffer with peer-to-peer stores
-    (``sg_exchange_push``), the ranks meet at a stream-ordered barrier, and each rank sums the few slots
-    that cover each plane (``sg_exchange_reduce``, rank order -> deterministic).  The staging buffers are
-    ``torch.distributed._symmetric_memory`` allocations (plumbing); the kernels are ours.  Two staging buffers
-    alternate so one barrier per exchange suffices.
+    those planes into its slot of every peer's staging buffer with peer-to-peer stores (fused into the adjoint's last
+    kernel, ``sg_evaluate_adjoint_push``, or ``sg_exchange_push``); then ONE kernel per rank
+    (``sg_exchange_wait_reduce``) tells the peers that the push has landed (release-store of an exchange counter into
+    their flag arrays), waits on the device for all peers' flags and sums the few slots that cover each plane (rank
+    order -> deterministic).  No host-side barrier, no collective call: the whole step is plain kernels and can be
+    captured in a CUDA graph.  Buffers are ``torch.distributed._symmetric_memory`` allocations (plumbing: allocation and
+    the exchange of the peer pointers only); the kernels and the barrier are ours.  Two staging buffers alternate.
     """
 
     def __init__(self, global_dims: Sequence[SplineDimension], Nout: int, rank: int, world_size: int, group=None):
@@ -95,6 +97,14 @@ class PeerGradientExchange:
             self.stage.append(t)
             self.hdl.append(h)
             self.peer_ptrs.append((_lib.C.c_void_p * world_size)(*[int(x) for x in h.buffer_ptrs]))
+        # flag array (peer-mapped, one uint64 per rank) and the local exchange counter of the C ABI's own barrier
+        self.flags = symm_mem.empty(max(world_size, 16), dtype=torch.int64, device=self.device)
+        self.flags.zero_()
+        self.flags_hdl = symm_mem.rendezvous(self.flags, grp)
+        self.peer_flags = (_lib.C.c_void_p * world_size)(*[int(x) for x in self.flags_hdl.buffer_ptrs])
+        self.sync = torch.zeros(8, dtype=torch.int64, device=self.device)          # SG_EXCHANGE_SYNC_BYTES
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=grp)                              # every rank's flags are zero before anybody signals
         self._k0s = _lib.i64_array(self.k0)
         self._nps = _lib.i64_array(self.np_)
         self.step = 0
@@ -103,57 +113,61 @@ class PeerGradientExchange:
     def adjoint_and_exchange_(self, grid, *, control_points: torch.Tensor, **kw) -> torch.Tensor:
         """Local ``evaluate_adjoint!`` with the gradient push FUSED into its last kernel
         (``sg_evaluate_adjoint_push``: finished control planes leave for the peers' staging slots while the kernel is still
-        running), then the barrier and the local reduce.  Same result as ``evaluate_adjoint_`` + ``exchange_``."""
+        running; the local partial gradient is not written at all), then signal + wait + reduce in one kernel.
+        Same result as ``evaluate_adjoint_`` + ``exchange_``."""
         from . import _lib
         b = self.step & 1
         self.step += 1
-        push = (b, self.peer_ptrs[b], self.world, self.rank, self.k0[self.rank], self.np_[self.rank], self.max_planes)
+        push = (b, self.peer_ptrs[b], self.world, self.rank, self.k0[self.rank], self.np_[self.rank], self.max_planes, 0)
         evaluate_adjoint_(grid, control_points=control_points, _push=push, **kw)
-        return self._barrier_and_reduce_(control_points, b, _lib.stream_ptr(self.device))
+        return self._wait_reduce_(control_points, b, _lib.stream_ptr(self.device))
 
-    def _barrier_and_reduce_(self, grad: torch.Tensor, b: int, st) -> torch.Tensor:
+    def _wait_reduce_(self, grad: torch.Tensor, b: int, st) -> torch.Tensor:
         from . import _lib
         C = _lib.C
-        key = ("reduce", b, grad.data_ptr())
+        key = ("wait_reduce", b, grad.data_ptr())
         prep = self._prepared.get(key)
         if prep is None:
             suf = _lib.suffix(self.dtype)
-            prep = (getattr(_lib.lib(), "sg_exchange_reduce_" + suf),
-                    (_lib.ptr(grad), _lib.ptr(self.stage[b]), C.c_int(self.world), self._k0s, self._nps,
-                     C.c_int64(self.plane_elems), C.c_int64(self.c_last), C.c_int(self.nout), C.c_int64(self.max_planes)))
+            prep = (getattr(_lib.lib(), "sg_exchange_wait_reduce_" + suf),
+                    (_lib.ptr(grad), _lib.ptr(self.stage[b]), _lib.ptr(self.flags), _lib.ptr(self.sync), self.peer_flags,
+                     C.c_int(self.world), C.c_int(self.rank), self._k0s, self._nps, C.c_int64(self.plane_elems),
+                     C.c_int64(self.c_last), C.c_int(self.nout), C.c_int64(self.max_planes)))
             if len(self._prepared) >= 16:
                 self._prepared.clear()
             self._prepared[key] = prep
-        self.hdl[b].barrier(channel=0)                      # stream-ordered, all ranks
-        _lib.check(prep[0](*prep[1], st), "sg_exchange_reduce")
+        _lib.check(prep[0](*prep[1], st), "sg_exchange_wait_reduce")
         return grad
 
     def exchange_(self, grad: torch.Tensor) -> torch.Tensor:
+        """Push kernel + (signal, wait, reduce) kernel on an already computed local partial gradient."""
         from . import _lib
         C = _lib.C
         b = self.step & 1
         self.step += 1
         st = _lib.stream_ptr(self.device)
-        key = (b, grad.data_ptr())
+        key = ("push", b, grad.data_ptr())
         prep = self._prepared.get(key)
         if prep is None:                                    # marshal once per (staging buffer, gradient array)
             suf = _lib.suffix(self.dtype)
-            lib = _lib.lib()
-            prep = (getattr(lib, "sg_exchange_push_" + suf),
+            prep = (getattr(_lib.lib(), "sg_exchange_push_" + suf),
                     (_lib.ptr(grad), self.peer_ptrs[b], C.c_int(self.world), C.c_int(self.rank), C.c_int64(self.plane_elems),
                      C.c_int64(self.c_last), C.c_int(self.nout), C.c_int64(self.k0[self.rank]), C.c_int64(self.np_[self.rank]),
-                     C.c_int64(self.max_planes)),
-                    getattr(lib, "sg_exchange_reduce_" + suf),
-                    (_lib.ptr(grad), _lib.ptr(self.stage[b]), C.c_int(self.world), self._k0s, self._nps,
-                     C.c_int64(self.plane_elems), C.c_int64(self.c_last), C.c_int(self.nout), C.c_int64(self.max_planes)))
+                     C.c_int64(self.max_planes)))
             if len(self._prepared) >= 16:
                 self._prepared.clear()
             self._prepared[key] = prep
-        push, push_args, reduce_, reduce_args = prep
-        _lib.check(push(*push_args, st), "sg_exchange_push")
-        self.hdl[b].barrier(channel=0)                      # stream-ordered, all ranks
-        _lib.check(reduce_(*reduce_args, st), "sg_exchange_reduce")
-        return grad
+        _lib.check(prep[0](*prep[1], st), "sg_exchange_push")
+        return self._wait_reduce_(grad, b, st)
+
+    def status(self):
+        """(exchanges completed on this rank, whether a wait ever timed out) -- blocking."""
+        from . import _lib
+        C = _lib.C
+        ep, to = C.c_ulonglong(0), C.c_int(0)
+        _lib.check(_lib.lib().sg_exchange_status(_lib.ptr(self.sync), C.byref(ep), C.byref(to), _lib.stream_ptr(self.device)),
+                   "sg_exchange_status")
+        return int(ep.value), bool(to.value)
 
 
 class SlabShardedGrid:
@@ -179,7 +193,8 @@ class SlabShardedGrid:
         if peer_exchange and world_size > 1:
             try:
                 self.exchange = PeerGradientExchange(self.global_dims, Nout, rank, world_size, group)
-                self.exchange_kind = "peer_memory_push_reduce (push fused into the adjoint's last kernel)"
+                self.exchange_kind = ("peer_memory_push + device-side flag barrier + reduce (push fused into the adjoint's last "
+                                      "kernel; signal, wait and reduce are one kernel)")
             except Exception as e:   # symmetric memory unavailable: keep the NCCL all-reduce
                 import warnings
                 warnings.warn(f"peer-memory gradient exchange unavailable ({e!r}); using the NCCL all-reduce")

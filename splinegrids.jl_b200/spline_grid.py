@@ -225,7 +225,7 @@ def evaluate_adjoint_(obj, *, derivative_order: Optional[Sequence[int]] = None, 
     control_points = grid.control_points if control_points is None else control_points
     eval_ = grid.eval if eval is None else eval
     cp = obtain(control_points)
-    # _push = (tag, peer_ptrs, world, rank, k0, np, max_planes): fused gradient push (distributed.PeerGradientExchange)
+    # _push = (tag, peer_ptrs, world, rank, k0, np, max_planes[, keep_local]): fused gradient push (distributed.PeerGradientExchange)
     key = _prepared_key("adj" if _push is None else ("adj_push", _push[0]), grid, der, cp, eval_)
     prep = grid.__dict__.get("_prepared", {}).get(key)
     if prep is None:
@@ -238,8 +238,10 @@ def evaluate_adjoint_(obj, *, derivative_order: Optional[Sequence[int]] = None, 
             fn = getattr(_lib.lib(), "sg_evaluate_adjoint_" + _lib.suffix(grid.dtype))
         else:
             fn = getattr(_lib.lib(), "sg_evaluate_adjoint_push_" + _lib.suffix(grid.dtype))
-            _, peer_ptrs, world, rank, k0, np_, max_planes = _push
-            args = args + (peer_ptrs, C.c_int(world), C.c_int(rank), C.c_int64(k0), C.c_int64(np_), C.c_int64(max_planes))
+            _, peer_ptrs, world, rank, k0, np_, max_planes = _push[:7]
+            keep_local = _push[7] if len(_push) > 7 else 1
+            args = args + (peer_ptrs, C.c_int(world), C.c_int(rank), C.c_int64(k0), C.c_int64(np_), C.c_int64(max_planes),
+                           C.c_int(keep_local))
         prep = (fn, args, grid.device.index, ws)
         _prepared_store(grid, key, prep)
     fn, args, dev_index = prep[0], prep[1], prep[2]

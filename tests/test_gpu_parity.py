@@ -377,6 +377,56 @@ def test_peer_exchange_kernels_single_device(S, ft):
         assert torch.equal(dev[r], dev[0])                          # rank-order summation: bit-identical on every rank
 
 
+@pytest.mark.parametrize("fused_signal", [False, True], ids=["signal-kernel", "signal-in-reduce"])
+def test_flag_synchronised_exchange_single_device(S, fused_signal):
+    """sg_exchange_signal / sg_exchange_wait_reduce (the C ABI's own device-side barrier) with all "ranks" simulated on
+    one device.  Every rank's wait needs every rank's signal, so the simulated ranks run on separate streams (signals
+    first when they are separate kernels); two consecutive exchanges check the device-resident exchange counter."""
+    import ctypes as C
+    lib = S._lib.lib()
+    rng = np.random.default_rng(18)
+    world, c1, c2, c_last, nout = 3, 16, 6, 20, 2
+    plane = c1 * c2
+    k0, npl = [0, 5, 12], [8, 10, 8]
+    max_planes = max(npl)
+    flags = [torch.zeros(16, dtype=torch.int64, device="cuda") for _ in range(world)]
+    syncs = [torch.zeros(8, dtype=torch.int64, device="cuda") for _ in range(world)]
+    peer_flags = (C.c_void_p * world)(*[t.data_ptr() for t in flags])
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    torch.cuda.synchronize()
+    for exchange in range(2):
+        grads = []
+        for r in range(world):
+            g = np.zeros((c1, c2, c_last, nout), order="F")
+            g[:, :, k0[r]:k0[r] + npl[r], :] = rng.random((c1, c2, npl[r], nout))
+            grads.append(g)
+        expected = sum(grads)
+        stages = [torch.full((world * nout * max_planes * plane,), float("nan"), dtype=torch.float64, device="cuda") for _ in range(world)]
+        peer = (C.c_void_p * world)(*[t.data_ptr() for t in stages])
+        dev = [S.to_device(g) for g in grads]
+        torch.cuda.synchronize()
+        for r in range(world):
+            st = C.c_void_p(streams[r].cuda_stream)
+            S._lib.check(lib.sg_exchange_push_f64(S._lib.ptr(dev[r]), peer, C.c_int(world), C.c_int(r), C.c_int64(plane), C.c_int64(c_last),
+                                                  C.c_int(nout), C.c_int64(k0[r]), C.c_int64(npl[r]), C.c_int64(max_planes), st), "push")
+            if not fused_signal:
+                S._lib.check(lib.sg_exchange_signal(peer_flags, C.c_int(world), C.c_int(r), S._lib.ptr(syncs[r]), st), "signal")
+        for r in range(world):
+            st = C.c_void_p(streams[r].cuda_stream)
+            S._lib.check(lib.sg_exchange_wait_reduce_f64(
+                S._lib.ptr(dev[r]), S._lib.ptr(stages[r]), S._lib.ptr(flags[r]), S._lib.ptr(syncs[r]),
+                peer_flags if fused_signal else None, C.c_int(world), C.c_int(r), S._lib.i64_array(k0), S._lib.i64_array(npl),
+                C.c_int64(plane), C.c_int64(c_last), C.c_int(nout), C.c_int64(max_planes), st), "wait_reduce")
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert rel_err(S.to_numpy(dev[r]), expected) <= 1e-14
+            assert torch.equal(dev[r], dev[0])
+            ep, to = C.c_ulonglong(0), C.c_int(0)
+            S._lib.check(lib.sg_exchange_status(S._lib.ptr(syncs[r]), C.byref(ep), C.byref(to), None), "status")
+            assert ep.value == exchange + 1 and to.value == 0
+            assert flags[r][:world].tolist() == [exchange + 1] * world
+
+
 @pytest.mark.parametrize("shape", [((12, 9, 40), (2, 3, 3), (128, 40, 96), "adjoint_march2"),
                                    ((9, 8, 40), (3, 2, 3), (40, 36, 96), "adjoint_passes")], ids=["fused", "fallback"])
 @pytest.mark.parametrize("world", [2, 3])
@@ -411,8 +461,10 @@ def test_fused_gradient_push_single_device(S, world, shape):
             ein = S.to_device(e[:, :, sh.lo:sh.hi, :])
             if fused:
                 S.evaluate_adjoint_(sh.local, eval=ein, control_points=g,
-                                    _push=(("t", r), peer, world, r, k0[r], npl[r], max_planes))
+                                    _push=(("t", r, fused), peer, world, r, k0[r], npl[r], max_planes, 0 if fused == "nolocal" else 1))
                 assert S.last_variant() == variant
+                if fused == "nolocal" and variant == "adjoint_march2":
+                    assert float(g.min()) == 3.0 and float(g.max()) == 3.0     # the local array was not touched
             else:
                 S.evaluate_adjoint_(sh.local, eval=ein, control_points=g)
                 S._lib.check(lib.sg_exchange_push_f64(S._lib.ptr(g), peer, C.c_int(world), C.c_int(r), C.c_int64(plane),
@@ -424,8 +476,10 @@ def test_fused_gradient_push_single_device(S, world, shape):
 
     st_fused, grads = run(True)
     st_plain, _ = run(False)
-    for a, b in zip(st_fused, st_plain):
+    st_nolocal, _ = run("nolocal")
+    for a, b, c in zip(st_fused, st_plain, st_nolocal):
         assert torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0))   # same slots written, same bits
+        assert torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(c, nan=-7.0))
     for r in range(world):
         S._lib.check(lib.sg_exchange_reduce_f64(S._lib.ptr(grads[r]), S._lib.ptr(st_fused[r]), C.c_int(world),
                                                 S._lib.i64_array(k0), S._lib.i64_array(npl), C.c_int64(plane),
