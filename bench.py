@@ -430,7 +430,7 @@ def main_gpu(args):
     # adjoint.  Its launch duration is measured live with CUDA events recorded by the library on the launch stream
     # right before / after the kernel (sg_profile_adjoint_main, include/splinegrids_b200.h).
     ms_main = None
-    if var_adj == "adjoint_march2":
+    if var_adj.startswith("adjoint_march2"):
         lib = S._lib.lib()
         lib.sg_profile_adjoint_main(1)
         samples = []

@@ -309,6 +309,34 @@ extern "C" float sg_profile_adjoint_main_ms(void)
 
 #define SG_M2_RTMAX 20
 #define SG_M2_NS 3
+
+// eval as a 3-D tensor (n1, n2, n3*nout) with boxes of 128 columns x (1..SG_M2_FAST_ROWS) rows x 1 plane
+typedef CUresult (*SgEncodeTiledFnA)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+template <typename T>
+static bool sg_m2_make_eval_maps(SgM2Maps &maps, const T *eval, int64_t n1, int64_t n2, int64_t n3nout)
+{
+    static SgEncodeTiledFnA enc = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<SgEncodeTiledFnA>(p);
+    }();
+    if (!enc || (n1 * sizeof(T)) % 16 != 0 || reinterpret_cast<uintptr_t>(eval) % 16 != 0) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)n1, (cuuint64_t)n2, (cuuint64_t)n3nout};
+    cuuint64_t strides[2] = {(cuuint64_t)n1 * sizeof(T), (cuuint64_t)n1 * n2 * sizeof(T)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    for (int r = 0; r < SG_M2_FAST_ROWS; ++r) {
+        cuuint32_t box[3] = {128, (cuuint32_t)(r + 1), 1};
+        if (enc(&maps.m[r], dt, 3, const_cast<T *>(eval), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    return true;
+}
 template <typename T, int P>
 static int sg_launch_march2(const SgAdj2Args<T> &m, int nout, cudaStream_t st)
 {
@@ -320,10 +348,17 @@ static int sg_launch_march2(const SgAdj2Args<T> &m, int nout, cudaStream_t st)
                         (double)m.n1 * (SG_M2_G2 + P) * m.tiles2 * (m.G3 + P) * m.chunks3 * nout < 4.0e9;   // 32-bit partial offsets
     if (tma_ok) {
         auto kern = sg_adj_march2_tma_kernel<T, P, SG_M2_G2, SG_M2_RTMAX, SG_M2_NS>;
-        const size_t smem = sizeof(T) * SG_M2_NS * SG_M2_RTMAX * 128;
+        const size_t smem = sizeof(T) * SG_M2_NS * SG_M2_RTMAX * 128 + 128;    // + slack for the 128-byte alignment of the ring
         SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (g_sg_prof_on) cudaEventRecord(g_sg_prof_ev[0], st);
-        kern<<<grid, 160, smem, st>>>(m);                                   // 4 consumer warps + 1 producer warp
+        SgM2Maps maps{};
+        const int use_maps = sg_env_int("SG_ADJ_M2_MAPS", 1) && sg_m2_make_eval_maps<T>(maps, m.X, m.n1, m.n2, m.n3 * nout) ? 1 : 0;
+        if (P == 3 && sizeof(T) == 8 && sg_env_int("SG_ADJ_M2_EXPER", 0) == 1) {   // measurement only (wrong results)
+            auto kx = sg_adj_march2_tma_kernel<T, P, SG_M2_G2, SG_M2_RTMAX, SG_M2_NS, 1>;
+            SG_CUDA(cudaFuncSetAttribute(kx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kx<<<grid, 160, smem, st>>>(m, maps, use_maps);
+        } else
+        kern<<<grid, 160, smem, st>>>(m, maps, use_maps);                   // 4 consumer warps + 1 producer warp
         if (g_sg_prof_on) { cudaEventRecord(g_sg_prof_ev[1], st); g_sg_prof_recorded = 1; }
         // tiles with more rows than the ring holds (normally none: one idle launch)
         sg_adj_march2_complement_kernel<T, P, SG_M2_G2, SG_M2_RS><<<148 * 4, 128, 0, st>>>(m, SG_M2_RTMAX, grid.x, grid.y, grid.z);

@@ -656,6 +656,24 @@ __device__ __forceinline__ void sg_bulk_g2s(void *dst, const void *src, unsigned
                  : "memory");
 }
 
+// 3-D tiled bulk tensor load (TMA) issued by one elected lane of a converged warp; completion on the mbarrier
+__device__ __forceinline__ void sg_m2_tma_load_3d_elect(uint32_t dst, const CUtensorMap *tmap, int c0, int c1, int c2, uint32_t bar)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "@p cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
+        "}\n" ::"r"(dst),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
+}
+// Tensor maps over eval viewed as (n1, n2, n3*nout) with boxes of 128 columns x (1 .. SG_M2_FAST_ROWS) rows x 1 plane: the rows of
+// one knot span of a tile are ONE tensor copy (4 copy instructions per plane instead of ~17 row copies).
+struct SgM2Maps {
+    CUtensorMap m[SG_M2_FAST_ROWS];
+};
+
 // Producer-warp primitives: executed by the WHOLE converged warp with warp-uniform operands (which then live in uniform
 // registers); one elected lane issues.  A lane-divergent caller (if (lane == 0) ...) costs ~25 instructions per copy.
 __device__ __forceinline__ void sg_m2_bulk_g2s_elect(uint32_t dst, const void *src, unsigned bytes, uint32_t bar)
@@ -703,15 +721,18 @@ __device__ __forceinline__ void sg_mbar_arrive(uint64_t *bar)
 // empty[st] : consumers -> producer, 128 arrivals once every consumer has read the stage
 // No block-wide barrier inside the plane loop; the (CTA-uniform) dimension-3 table rows are staged per piece of
 // MAXPL planes.
-template <typename T, int P, int G2, int RTMAX, int NS>
-__global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_constant__ SgAdj2Args<T> a)
+template <typename T, int P, int G2, int RTMAX, int NS, int EXPER = 0>
+__global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_constant__ SgAdj2Args<T> a, const __grid_constant__ SgM2Maps maps,
+                                                                   int use_maps)
 {
     if (!sg_adj_path_active(a.hdr, a.path)) return;
     constexpr int S = G2 + P;
     constexpr int MAXPL = 128;                                          // planes per staged piece of dim-3 tables
     constexpr int CW = 128;                                             // columns per CTA == consumer threads
-    extern __shared__ __align__(128) unsigned char sg_smem2[];
-    T *xs = reinterpret_cast<T *>(sg_smem2);                            // [NS][RTMAX][CW]
+    // The ring is aligned to 128 bytes by hand (the launcher adds the slack).  Claiming __align__(128) on the extern array
+    // would let the compiler fold the adjustment away, while the run-time base is only 16-byte aligned.
+    extern __shared__ __align__(16) unsigned char sg_smem2[];
+    T *xs = reinterpret_cast<T *>(sg_smem2 + ((128u - (sg_smem_u32(sg_smem2) & 127u)) & 127u));   // [NS][RTMAX][CW]
     __shared__ __align__(16) T b3s[MAXPL * (P + 1)];
     __shared__ int s3s[MAXPL];
     __shared__ int row0[G2 + 1];
@@ -807,6 +828,23 @@ __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_
             int ra[G2], rn[G2];
 #pragma unroll
             for (int g = 0; g < G2; ++g) { ra[g] = row0[g] - r_first; rn[g] = row0[g + 1] - row0[g]; }
+            if (use_maps) {
+                // one tensor copy per knot span: box = 128 columns x rn[g] rows (columns past n1 are zero-filled by the TMA unit)
+                const unsigned stage_tx = (unsigned)(CW * sizeof(T)) * (unsigned)n_rows;
+                const int pl0 = (int)(a.n3 * o + j3_lo);                // first plane of the chunk in the (n1, n2, n3*nout) view
+                for (int p = 0; p < np_total; ++p) {
+                    if (p >= NS) sg_m2_mbar_wait_u(empty_u + (uint32_t)st * 8u, ph ^ 1u);
+                    const uint32_t fb = full_u + (uint32_t)st * 8u;
+                    sg_m2_expect_tx_elect(fb, stage_tx);
+                    const uint32_t dst = xs_u + (uint32_t)st * (uint32_t)(RTMAX * CW * sizeof(T));
+#pragma unroll
+                    for (int g = 0; g < G2; ++g)
+                        if (rn[g] > 0)                                  // warp-uniform
+                            sg_m2_tma_load_3d_elect(dst + (uint32_t)(g * RS5 * CW * sizeof(T)), &maps.m[rn[g] - 1], (int)j1_0, r_first + ra[g], pl0 + p, fb);
+                    if (++st == NS) { st = 0; ph ^= 1u; }
+                }
+                return;
+            }
             const unsigned stage_tx = row_bytes * (unsigned)n_rows;
             for (int p = 0; p < np_total; ++p) {
                 if (p >= NS) sg_m2_mbar_wait_u(empty_u + (uint32_t)st * 8u, ph ^ 1u);   // every consumer warp has read this stage's previous plane
@@ -847,6 +885,7 @@ __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_
                 for (int g = 0; g < G2; ++g) {
 #pragma unroll
                     for (int q = 0; q < RS5; ++q) {
+                        if (EXPER == 1 && (g > 0 || q > 0)) continue;   // (measurement only: no contraction of dimension 2)
                         const T x = xst[(g * RS5 + q) * CW];
 #pragma unroll
                         for (int k = 0; k <= P; ++k) T2[g + k] = fma(b2pad[(g * RS5 + q) * (P + 1) + k], x, T2[g + k]);

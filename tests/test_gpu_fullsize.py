@@ -68,7 +68,7 @@ def test_c3_full_size_3d_cubic_float64(S):
     y.copy_(torch.rand(y.shape, dtype=y.dtype, device="cuda", generator=g))
     grad = torch.zeros_like(cp)
     S.evaluate_adjoint_(grid, eval=y, control_points=grad)
-    assert S.last_variant() == "adjoint_march2"
+    assert S.last_variant().startswith("adjoint_march2")
     lhs, rhs = _dot(ev, y), _dot(cp, grad)
     assert abs(lhs - rhs) <= 1e-11 * abs(lhs)
     # ... and the multi-pass pipeline gives the same gradient
@@ -93,7 +93,7 @@ def test_c3_full_size_3d_cubic_float64(S):
     y.zero_()
     y[:, :, torch.tensor(planes, device="cuda"), :] = S.to_device(y_np)
     S.evaluate_adjoint_(grid, eval=y, control_points=grad)
-    assert S.last_variant() == "adjoint_march2"
+    assert S.last_variant().startswith("adjoint_march2")
     tabs = [np.asfortranarray(S.to_numpy(sd.eval)) for sd in dims]
     idxs = [np.ascontiguousarray(S.to_numpy(sd.sample_indices)) for sd in dims]
     tabs[2], idxs[2] = np.asfortranarray(tabs[2][planes]), np.ascontiguousarray(idxs[2][planes])

@@ -80,7 +80,7 @@ def _worker(rank: int, world: int, port: int, out_dir: str):
             grad.fill_(float("nan"))
             sh.evaluate_adjoint_(eval=e_loc, control_points=grad)
             torch.cuda.synchronize()
-            assert S.last_variant() == "adjoint_march2"
+            assert S.last_variant().startswith("adjoint_march2")
             assert float((grad - ref).norm() / ref.norm()) <= 1e-13, it
             got = S.to_numpy(grad)
             assert np.linalg.norm(got - gref) / np.linalg.norm(gref) <= 1e-12
@@ -106,9 +106,10 @@ def _worker(rank: int, world: int, port: int, out_dir: str):
         dist.all_gather_object(counts, ep)
         assert len(set(counts)) == 1, counts                        # every rank completed the same number of exchanges
         # every rank holds bit-identical gradients (rank-order summation)
-        g0 = grad.clone()
+        mine = grad.permute(*reversed(range(grad.dim()))).contiguous()   # column-major array as a contiguous tensor
+        g0 = mine.clone()
         dist.broadcast(g0, 0)
-        assert torch.equal(g0, grad)
+        assert torch.equal(g0, mine)
         Path(out_dir, f"ok{rank}").write_text("ok")
     finally:
         dist.destroy_process_group()
