@@ -144,6 +144,35 @@ int sg_evaluate_adjoint_f64(double *cp, int nin, const int64_t *n_samples, const
                             const int *mdo, const int *der, const double *eval, const double *weights_or_null,
                             void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- adjoint plan (the "plan/workspace handle for the adjoint's inverse sample map" of the operator interface) ----------
+ * sg_evaluate_adjoint rebuilds the inverse sample map (first sample of every knot span, gather tables) on every call
+ * and decides on device whether the span indices are monotone, so it must also launch its fallback kernels.  A fitting
+ * loop calls evaluate_adjoint! thousands of times on the same SplineDimensions: a plan runs that preparation ONCE, keeps
+ * the tables in device memory owned by the handle, reads the few decision flags back (this call synchronises `stream`)
+ * and lets sg_evaluate_adjoint_planned launch exactly the kernels that are needed: for an eligible 3-D grid the fused
+ * double march (all three contractions in one pass over the sample array + one halo-sum kernel, 2 launches).
+ * The plan captures the ARGUMENTS of sg_evaluate_adjoint (sizes, table / index pointers, derivative_order); it is valid
+ * as long as those device arrays are unchanged -- re-create it after evaluate!(spline_dimension) (src/spline_dimension.jl:231)
+ * or when derivative_order changes.  Results are identical to sg_evaluate_adjoint up to summation order.
+ * peer_stage_or_null != NULL: fused gradient push as in sg_evaluate_adjoint_push below. */
+typedef struct sg_adjoint_plan sg_adjoint_plan;
+int sg_adjoint_plan_create_f32(sg_adjoint_plan **plan, int nin, const int64_t *n_samples, const int64_t *n_cp, int nout,
+                               const float *const *tables, const int32_t *const *indices, const int *degree,
+                               const int *mdo, const int *der, int rational, void *stream);
+int sg_adjoint_plan_create_f64(sg_adjoint_plan **plan, int nin, const int64_t *n_samples, const int64_t *n_cp, int nout,
+                               const double *const *tables, const int32_t *const *indices, const int *degree,
+                               const int *mdo, const int *der, int rational, void *stream);
+int sg_adjoint_plan_destroy(sg_adjoint_plan *plan);
+/* what the plan found: span indices monotone in every dimension; column-block tables of the fused pipeline fit; largest
+ * number of samples in one knot span of dimension 2 (any pointer may be NULL) */
+int sg_adjoint_plan_info(const sg_adjoint_plan *plan, int *monotone, int *fused_tables_fit, int *rows2_max);
+int sg_evaluate_adjoint_planned_f32(const sg_adjoint_plan *plan, float *cp, const float *eval, const float *weights_or_null,
+                                    void *workspace, size_t workspace_bytes, void *const *peer_stage_or_null, int world,
+                                    int my_rank, int64_t k0, int64_t np, int64_t max_planes, int keep_local, void *stream);
+int sg_evaluate_adjoint_planned_f64(const sg_adjoint_plan *plan, double *cp, const double *eval, const double *weights_or_null,
+                                    void *workspace, size_t workspace_bytes, void *const *peer_stage_or_null, int world,
+                                    int my_rank, int64_t k0, int64_t np, int64_t max_planes, int keep_local, void *stream);
+
 /* ---- K5 refinement_matrix_array_mul_kernel -- src/refinement_matrix.jl:365-403, mult! :421-445
  * (row window helpers src/refinement_matrix.jl:103-125, src/utils.jl:204-235)
  * Y[I] = sum_{J in window(I)} B[J] * prod_{d refined} A_d[I_d, J_d].  ndims = rank of Y and B (incl. Nout).

@@ -10,7 +10,7 @@ There is no CPU fallback: every compute path needs the CUDA library and a CUDA d
 from . import _lib
 from ._lib import SplineGridsB200Error, last_variant, launch_count, launch_count_reset, set_kernel_policy
 from .arrays import (as_colmajor, is_colmajor, jl_empty, jl_ones, jl_zeros, reshape_colmajor, to_device, to_numpy)
-from .config import asynchronous, is_synchronous, set_synchronous
+from .config import adjoint_plans, asynchronous, is_synchronous, set_adjoint_plans, set_synchronous
 from .control_points import (DefaultControlPoints, LocallyRefinedControlPoints, LocalRefinement,
                              activate_local_control_point_range_, activate_local_refinement_, copyto_,
                              deactivate_overwritten_control_points_, get_n_control_points, obtain)
@@ -34,5 +34,6 @@ __all__ = [
     "copyto_", "SplineGridLinearMap", "SlabShardedGrid", "PeerGradientExchange", "allreduce_gradient_", "slab_bounds", "to_device", "to_numpy",
     "jl_zeros", "jl_ones", "jl_empty", "reshape_colmajor", "is_colmajor", "as_colmajor", "set_synchronous",
     "is_synchronous", "asynchronous", "set_kernel_policy", "last_variant", "launch_count", "launch_count_reset",
-    "SplineGridsError", "SplineGridsB200Error", "boehm_refinement_matrix", "CapturedCalls",
+    "SplineGridsError", "SplineGridsB200Error", "boehm_refinement_matrix", "CapturedCalls", "set_adjoint_plans",
+    "adjoint_plans",
 ]

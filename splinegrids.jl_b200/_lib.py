@@ -53,6 +53,8 @@ def lib() -> C.CDLL:
         _lib.sg_set_kernel_policy.argtypes = [C.c_int]
         _lib.sg_last_variant.restype = C.c_char_p
         _lib.sg_evaluate_adjoint_workspace_bytes.restype = C.c_size_t
+        _lib.sg_adjoint_plan_destroy.argtypes = [C.c_void_p]
+        _lib.sg_adjoint_plan_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         _lib.sg_profile_adjoint_main.restype = None
         _lib.sg_profile_adjoint_main.argtypes = [C.c_int]
         _lib.sg_profile_adjoint_main_ms.restype = C.c_float

@@ -33,3 +33,18 @@ def asynchronous():
 def after_launch(device=None) -> None:
     if _synchronous:
         torch.cuda.current_stream(device).synchronize()
+
+
+# evaluate_adjoint! through an adjoint plan (sg_adjoint_plan_*): the inverse sample map is built once per grid and
+# derivative order instead of on every call, and exactly the kernels that are needed are launched.  Switch off to
+# exercise the plain sg_evaluate_adjoint entry point (all decisions on device, fallback kernels launched).
+_adjoint_plans = True
+
+
+def set_adjoint_plans(flag: bool) -> None:
+    global _adjoint_plans
+    _adjoint_plans = bool(flag)
+
+
+def adjoint_plans() -> bool:
+    return _adjoint_plans

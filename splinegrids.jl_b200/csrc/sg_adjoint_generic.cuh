@@ -15,6 +15,11 @@ struct SgSpanStarts {
     // of its support, the number of samples, and the first SG_GATHER_RMAX basis weights B1[lo + r, i - span + p]
     int32_t *g_lo;     // [c_1][2] = (lo, len)
     T *g_w;            // [SG_GATHER_RMAX][c_1]
+    // per-column-block tables of dimension 1 for the fused double march (sg_adjoint_march2g.cuh); bt_hdr == nullptr: none
+    SgM2gBlockHdr *bt_hdr;   // [nb1]
+    int32_t *bt_lol;         // [nb1][icap]  (first sample of the support relative to the block | number of samples << 16)
+    T *bt_w;                 // [nb1][rmcap][icap] gather weights B1[lo + r, i - span + p], zero beyond the support
+    int icap, rmcap, nb1;
 };
 #define SG_GATHER_RMAX 20
 
@@ -22,6 +27,57 @@ template <typename T>
 __global__ void sg_adjoint_prep_kernel(const __grid_constant__ SgGridArgs<T> a, const __grid_constant__ SgSpanStarts<T> ss,
                                        SgAdjointHeader *hdr)
 {
+    if ((int)blockIdx.y == a.nin + 1) {
+        // second extra row of blocks: the column-block tables of the fused double march.  One CUDA block per column
+        // block of 128 samples (grid-stride); a thread owns one local control index.
+        if (ss.bt_hdr == nullptr) return;
+        __shared__ int s_ilo, s_ni, s_rm;
+        const int64_t n0 = a.n_samples[0], c0 = a.n_cp[0];
+        const int p0 = a.degree[0];
+        const int32_t *__restrict__ idx0 = a.index[0];
+        for (int jb = blockIdx.x; jb < ss.nb1; jb += gridDim.x) {
+            const int64_t j_lo = (int64_t)jb * 128, j_hi = min(j_lo + 128, n0);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                s_ilo = idx0[j_lo] - p0;
+                s_ni = idx0[j_hi - 1] - s_ilo + 1;
+                s_rm = 0;
+            }
+            __syncthreads();
+            const int ilo = s_ilo, ni = s_ni;
+            const bool fits = ni >= 1 && ni <= ss.icap;
+            for (int li = threadIdx.x; li < min(ni, ss.icap); li += blockDim.x) {
+                const int64_t i = (int64_t)ilo + li;                    // 1-based control index
+                const int64_t s0 = i > p0 + 1 ? i : p0 + 1, s1 = (i + p0 < c0 ? i + p0 : c0) + 1;
+                int64_t lo = j_lo, hi = j_hi;                           // first sample of the block with span >= s0
+                while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (idx0[mid] >= s0) hi = mid; else lo = mid + 1; }
+                const int64_t first = lo;
+                hi = j_hi;                                              // first sample of the block with span >= s1
+                while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (idx0[mid] >= s1) hi = mid; else lo = mid + 1; }
+                const int len = (int)(lo - first);
+                atomicMax(&s_rm, len);
+                const int len_w = min(len, ss.rmcap);
+                ss.bt_lol[(int64_t)jb * ss.icap + li] = (int32_t)(first - j_lo) | (len_w << 16);
+                T *__restrict__ wp = ss.bt_w + (int64_t)jb * ss.rmcap * ss.icap + li;
+                for (int r = 0; r < ss.rmcap; ++r) {
+                    T w = T(0);
+                    if (r < len_w) {
+                        const int k = min(max((int)(i - idx0[first + r] + p0), 0), p0);   // clamp: garbage-safe
+                        w = a.table[0][first + r + n0 * k];
+                    }
+                    wp[(int64_t)r * ss.icap] = w;
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                SgM2gBlockHdr bh;
+                bh.i1_lo = ilo; bh.ni = fits ? ni : 1; bh.rm = s_rm; bh.pad = 0;
+                ss.bt_hdr[jb] = bh;
+                if (!fits || s_rm > ss.rmcap) hdr->m2g_bad = 1;
+            }
+        }
+        return;
+    }
     if ((int)blockIdx.y == a.nin) {
         // extra row of blocks: the gather table of dimension 1 (binary searches of its own: no dependence on start[])
         if (ss.g_lo == nullptr) return;
@@ -71,6 +127,7 @@ __global__ void sg_adjoint_prep_kernel(const __grid_constant__ SgGridArgs<T> a, 
         hdr->span_first[d] = idx[0];
         hdr->span_last[d] = idx[n - 1];
     }
+    int rows_max = 0;
     for (int64_t s = tid; s <= a.n_cp[d] + 1; s += stride) {
         int64_t lo = 0, hi = n;  // first j with idx[j] >= s
         while (lo < hi) {
@@ -78,7 +135,14 @@ __global__ void sg_adjoint_prep_kernel(const __grid_constant__ SgGridArgs<T> a, 
             if (idx[mid] >= s) hi = mid; else lo = mid + 1;
         }
         ss.start[d][s] = (int32_t)lo;
+        if (d == 1) {                                                   // samples in span s (3-D double march: ring row slots)
+            int64_t l2 = lo;
+            hi = n;
+            while (l2 < hi) { const int64_t mid = (l2 + hi) >> 1; if (idx[mid] >= s + 1) hi = mid; else l2 = mid + 1; }
+            rows_max = max(rows_max, (int)(l2 - lo));
+        }
     }
+    if (d == 1 && rows_max > 0) atomicMax(&hdr->rows2_max, rows_max);
 }
 
 // One thread per control point; gathers prod_d B_d[J_d, i_d - span(J_d) + p_d] * eval[J, o]

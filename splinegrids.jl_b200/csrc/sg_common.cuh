@@ -108,7 +108,15 @@ struct SgAdjointHeader {
     int m2_skipped;   // set by the TMA-fed double march when it leaves a tile to the register kernel (complement pass)
     int span_first[SG_MAX_DIMS];   // span of the first / last sample of every dimension (1-based), written by the
     int span_last[SG_MAX_DIMS];    // prep kernel: the control indices a (slab of a) grid can touch are [first-p, last]
-    int pad[62 - 2 * SG_MAX_DIMS];
+    int m2g_bad;      // set by the prep kernel when a column block's table of dimension 1 does not fit (fused double march)
+    int rows2_max;    // largest number of samples in one knot span of dimension 2 (prep kernel; 3-D grids)
+    int pad[60 - 2 * SG_MAX_DIMS];
+};
+static_assert(sizeof(SgAdjointHeader) == 256, "adjoint workspace header is 256 bytes");
+// Fused double march (sg_adjoint_march2g.cuh): per column block of 128 samples of dimension 1, the control indices it
+// touches [i1_lo, i1_lo + ni) (1-based) and the longest support (in samples of the block) of one of them.
+struct SgM2gBlockHdr {
+    int i1_lo, ni, rm, pad;
 };
 // Fused adjoint: control-index slots reserved per warp tile of TS = 32*V samples of dimension 1.  A tile
 // touches at most TS + p control indices (every sample in its own span), p <= 5 -> TS + 8 (keeps 16-byte alignment).

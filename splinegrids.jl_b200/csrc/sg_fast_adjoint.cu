@@ -8,6 +8,7 @@
 #include "sg_fast.cuh"
 #include "sg_fast_adjoint.cuh"
 #include "sg_adjoint_post2.cuh"
+#include "sg_adjoint_march2g.cuh"
 #include "sg_fast_eval.cuh"
 
 static int sg_env_int(const char *name, int dflt)
@@ -33,7 +34,7 @@ struct SgAdjPlan {
 
 static size_t sg_al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static SgAdjPlan sg_adjoint_plan(int nin, const int64_t *n_samples, const int64_t *n_cp, int nout, const int *degree,
+static SgAdjPlan sg_adjoint_pass_plan(int nin, const int64_t *n_samples, const int64_t *n_cp, int nout, const int *degree,
                                  int elem_size)
 {
     SgAdjPlan pl{};
@@ -154,7 +155,7 @@ static int sg_run_multipass(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T>
                             const T *weights, char *ws, int path, cudaStream_t st)
 {
     const bool rational = weights != nullptr;
-    const SgAdjPlan pl = sg_adjoint_plan(a.nin, a.n_samples, a.n_cp, a.nout, a.degree, (int)sizeof(T));
+    const SgAdjPlan pl = sg_adjoint_pass_plan(a.nin, a.n_samples, a.n_cp, a.nout, a.degree, (int)sizeof(T));
     for (int k = 0; k < pl.npassA; ++k) {
         const SgAdjPass &ps = pl.pass[k];
         if (ps.outer > 65535 || ps.nchunks > 65535 || (ps.nchunks > 1 && ps.c_d > 65535)) return SG_ERR_UNSUPPORTED;
@@ -228,6 +229,8 @@ struct SgMarch2Plan {
     bool ok;
     int G2, tiles2, G3, chunks3;
     size_t part_off, r_off, bytes;
+    SgM2gDims g;                 // fused variant (dimension 1 contracted in the march kernel's epilogue)
+    size_t bytes_unfused;
 };
 #define SG_M2_G2 4
 #define SG_M2_RS 6
@@ -266,9 +269,36 @@ static SgMarch2Plan sg_adjoint_march2_plan(int nin, const int64_t *n_samples, co
     mp.part_off = off;
     off += sg_al256((size_t)n_samples[0] * (mp.G2 + P) * mp.tiles2 * (mp.G3 + P) * mp.chunks3 * nout * elem_size);
     mp.r_off = off;                                                     // (no intermediate array any more: the post kernel reads the partials)
-    mp.bytes = off;
+    mp.bytes = mp.bytes_unfused = off;
+    mp.g = sg_m2g_dims(nin, n_samples, n_cp, degree, rational);
+    if (mp.g.ok) {
+        const double elems = (double)mp.g.icap * (mp.G2 + P) * mp.tiles2 * (mp.G3 + P) * mp.chunks3 * mp.g.nb1 * nout;
+        if (elems < 4.0e9) mp.bytes = std::max(mp.bytes, sg_al256((size_t)elems * elem_size));
+        else mp.g.ok = false;
+    }
     mp.ok = true;
     return mp;
+}
+
+// Fused double march: eligibility and table sizes from the shape alone (the prep kernel checks the data on device).
+// Worth it when dimension 1 has at least ~2 samples per knot span (a block of 128 columns then leaves <= ~70 control
+// indices); icap / rmcap leave a factor 2 of slack over equispaced samples.
+SgM2gDims sg_m2g_dims(int nin, const int64_t *n_samples, const int64_t *n_cp, const int *degree, bool rational)
+{
+    SgM2gDims g{};
+    g.ok = false;
+    if (rational || nin != 3 || sg_env_int("SG_ADJ_M2G", 0) == 0) return g;   // opt-in (SG_ADJ_M2G=1): measured slower than the unfused pipeline, see DESIGN.md
+    const int P = degree[1];
+    if (degree[2] != P || P < 1 || P > 3 || degree[0] < 1 || degree[0] > 5) return g;
+    const int64_t n1 = n_samples[0], nsp1 = n_cp[0] - degree[0];
+    if (n1 < 128 || n1 < 2 * nsp1) return g;
+    const int64_t est_spans = (128 * nsp1 + n1 - 1) / n1;
+    g.icap = (int)std::min<int64_t>(((2 * est_spans + degree[0] + 2 + 7) / 8) * 8, 136);
+    g.rmcap = (int)std::min<int64_t>((degree[0] + 1) * ((2 * n1 + nsp1 - 1) / nsp1) + 2, 128);
+    g.nb1 = (int)((n1 + 127) / 128);
+    if ((int64_t)g.nb1 * g.rmcap * g.icap > (int64_t)1 << 26) return g;
+    g.ok = true;
+    return g;
 }
 
 
@@ -276,7 +306,7 @@ size_t sg_adjoint_fast_scratch_bytes(int nin, const int64_t *n_samples, const in
                                      int elem_size)
 {
     if (!sg_adjoint_fast_supported(nin, degree, false)) return 0;
-    const size_t a = sg_adjoint_plan(nin, n_samples, n_cp, nout, degree, elem_size).bytes;
+    const size_t a = sg_adjoint_pass_plan(nin, n_samples, n_cp, nout, degree, elem_size).bytes;
     const SgMarch2Plan mp = sg_adjoint_march2_plan(nin, n_samples, n_cp, nout, degree, elem_size, false);
     // the pipelines never run together: they share the scratch
     return std::max(a, mp.ok ? mp.bytes : (size_t)0);
@@ -338,7 +368,7 @@ static bool sg_m2_make_eval_maps(SgM2Maps &maps, const T *eval, int64_t n1, int6
     return true;
 }
 template <typename T, int P>
-static int sg_launch_march2(const SgAdj2Args<T> &m, int nout, cudaStream_t st)
+static int sg_launch_march2(const SgAdj2Args<T> &m, int nout, const SgAdjKnown &known, cudaStream_t st)
 {
     dim3 grid((unsigned)((m.n1 + 127) / 128), (unsigned)m.tiles2, (unsigned)(m.chunks3 * nout));
     // TMA-fed ring: bulk copies need 16-byte aligned rows; rows per tile are data dependent, so the expected count must
@@ -360,7 +390,11 @@ static int sg_launch_march2(const SgAdj2Args<T> &m, int nout, cudaStream_t st)
         } else
         kern<<<grid, 160, smem, st>>>(m, maps, use_maps);                   // 4 consumer warps + 1 producer warp
         if (g_sg_prof_on) { cudaEventRecord(g_sg_prof_ev[1], st); g_sg_prof_recorded = 1; }
-        // tiles with more rows than the ring holds (normally none: one idle launch)
+        // tiles with more rows than the ring holds (normally none: one idle launch; a plan knows and skips it)
+        if (known.planned && known.rows2_max <= SG_M2_FAST_ROWS) {
+            g_sg_launches.fetch_add(1);
+            return SG_OK;
+        }
         sg_adj_march2_complement_kernel<T, P, SG_M2_G2, SG_M2_RS><<<148 * 4, 128, 0, st>>>(m, SG_M2_RTMAX, grid.x, grid.y, grid.z);
         g_sg_launches.fetch_add(2);
         return SG_OK;
@@ -370,11 +404,89 @@ static int sg_launch_march2(const SgAdj2Args<T> &m, int nout, cudaStream_t st)
     return SG_OK;
 }
 
+// ---- fused double march (sg_adjoint_march2g.cuh): planned calls only -- the plan has checked on the host that the
+// spans are monotone, every span of dimension 2 fits the ring's row slots and the column-block tables fit ------------
+size_t sg_m2_uni_bytes(int elem_size) { return elem_size == 4 ? sizeof(SgM2Uni<float>) : sizeof(SgM2Uni<double>); }
+
+template <typename T>
+static bool sg_m2_uni_fill_t(SgM2Uni<T> *u, const T *table2, int64_t n2, int P, const int32_t *start2, int64_t c2,
+                             const int32_t *start3, int64_t c3, int sf3, int sl3)
+{
+    if (n2 * (P + 1) > (int64_t)(SG_M2U_B2_BYTES / sizeof(T)) || c2 + 2 > SG_M2U_STARTS || c3 + 2 > SG_M2U_STARTS) return false;
+    for (int64_t r = 0; r < n2; ++r)
+        for (int k = 0; k <= P; ++k) u->b2[r * (P + 1) + k] = table2[r + n2 * k];
+    for (int64_t s = 0; s <= c2 + 1; ++s) u->start2[s] = start2[s];
+    for (int64_t s = 0; s <= c3 + 1; ++s) u->start3[s] = start3[s];
+    u->span_first3 = sf3; u->span_last3 = sl3;
+    return true;
+}
+bool sg_m2_uni_fill(void *uni, int elem_size, const void *table2_host, int64_t n2, int P, const int32_t *start2_host, int64_t c2,
+                    const int32_t *start3_host, int64_t c3, int span_first3, int span_last3)
+{
+    if (elem_size == 4)
+        return sg_m2_uni_fill_t<float>(static_cast<SgM2Uni<float> *>(uni), static_cast<const float *>(table2_host), n2, P, start2_host, c2,
+                                       start3_host, c3, span_first3, span_last3);
+    return sg_m2_uni_fill_t<double>(static_cast<SgM2Uni<double> *>(uni), static_cast<const double *>(table2_host), n2, P, start2_host, c2,
+                                    start3_host, c3, span_first3, span_last3);
+}
+
+template <typename T, int P>
+static int sg_launch_march2g(T *cp, const SgAdj2gArgs<T> &m, const SgSpanStarts<T> &ss, int nout, int64_t c1, const SgM2Maps &maps,
+                             const SgM2Uni<T> *uni, cudaStream_t st)
+{
+    const size_t smem = sizeof(T) * ((size_t)SG_M2_NS * SG_M2_RTMAX * 128 + (size_t)(SG_M2_G2 + P) * SG_M2G_EP) + 128;
+    dim3 grid((unsigned)m.nb1, (unsigned)m.tiles2, (unsigned)(m.chunks3 * nout));
+    if (g_sg_prof_on) cudaEventRecord(g_sg_prof_ev[0], st);
+    if (uni != nullptr && sg_env_int("SG_ADJ_M2_UNI", 1)) {             // weights of dimension 2 through the uniform datapath
+        auto kern = sg_adj_march2g_kernel<T, P, SG_M2_G2, SG_M2_RTMAX, SG_M2_NS, true>;
+        SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 160, smem, st>>>(m, maps, *uni);                   // 4 consumer warps + 1 producer warp
+    } else {
+        auto kern = sg_adj_march2g_kernel<T, P, SG_M2_G2, SG_M2_RTMAX, SG_M2_NS, false>;
+        SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 160, smem, st>>>(m, maps, SgM2UniNone<T>{});
+    }
+    if (g_sg_prof_on) { cudaEventRecord(g_sg_prof_ev[1], st); g_sg_prof_recorded = 1; }
+    dim3 cgrid((unsigned)((m.tiles2 + 1) * sg_blocks(c1, 128)), (unsigned)m.c3, (unsigned)nout);
+    SgPushSpec ps{};                                                    // world == 0: plain adjoint
+    if (g_sg_push != nullptr) { ps = *g_sg_push; g_sg_push_done = true; }
+    sg_adj_combine2g_kernel<T, P, SG_M2_G2><<<cgrid, 128, 0, st>>>(cp, m.Y, ss.g_lo, m.bt_hdr, m.hdr, c1, m.c2, m.c3, m.tiles2, m.G3, m.chunks3,
+                                                                   m.icap, m.nb1, ps);
+    g_sg_launches.fetch_add(2);
+    return SG_OK;
+}
+
+template <typename T>
+static int sg_run_march2g(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &ss, SgAdjointHeader *hdr, const T *eval,
+                          const SgMarch2Plan &mp, char *ws, const SgM2Maps &maps, const SgM2Uni<T> *uni, cudaStream_t st)
+{
+    SgAdj2gArgs<T> m{};
+    m.X = eval; m.Y = reinterpret_cast<T *>(ws + mp.part_off);
+    m.table2 = a.table[1]; m.table3 = a.table[2]; m.index3 = a.index[2];
+    m.start2 = ss.start[1]; m.start3 = ss.start[2]; m.hdr = hdr;
+    m.bt_hdr = ss.bt_hdr; m.bt_lol = ss.bt_lol; m.bt_w = ss.bt_w;
+    m.n1 = a.n_samples[0]; m.n2 = a.n_samples[1]; m.n3 = a.n_samples[2]; m.c2 = a.n_cp[1]; m.c3 = a.n_cp[2];
+    m.tiles2 = mp.tiles2; m.G3 = mp.G3; m.chunks3 = mp.chunks3; m.icap = ss.icap; m.rmcap = ss.rmcap; m.nb1 = ss.nb1;
+    switch (a.degree[1]) {
+        case 1: return sg_launch_march2g<T, 1>(cp, m, ss, a.nout, a.n_cp[0], maps, uni, st);
+        case 2: return sg_launch_march2g<T, 2>(cp, m, ss, a.nout, a.n_cp[0], maps, uni, st);
+        default: return sg_launch_march2g<T, 3>(cp, m, ss, a.nout, a.n_cp[0], maps, uni, st);
+    }
+}
+
 template <typename T>
 static int sg_run_march2(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &ss, SgAdjointHeader *hdr, const T *eval,
-                         const SgMarch2Plan &mp, char *ws, cudaStream_t st)
+                         const SgMarch2Plan &mp, char *ws, const SgAdjKnown &known, const char **variant, cudaStream_t st)
 {
     const int P = a.degree[1];
+    *variant = "adjoint_march2";
+    if (known.planned && known.fused_ok && mp.g.ok && ss.bt_hdr != nullptr && known.rows2_max <= SG_M2_FAST_ROWS) {
+        SgM2Maps maps{};
+        if (sg_m2_make_eval_maps<T>(maps, eval, a.n_samples[0], a.n_samples[1], a.n_samples[2] * a.nout)) {
+            *variant = "adjoint_march2_fused";
+            return sg_run_march2g<T>(cp, a, ss, hdr, eval, mp, ws, maps, static_cast<const SgM2Uni<T> *>(known.uni), st);
+        }
+    }
     SgAdj2Args<T> m{};
     T *part = reinterpret_cast<T *>(ws + mp.part_off);
     m.X = eval; m.Y = part; m.table2 = a.table[1]; m.table3 = a.table[2]; m.index3 = a.index[2];
@@ -383,9 +495,9 @@ static int sg_run_march2(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &s
     m.tiles2 = mp.tiles2; m.G3 = mp.G3; m.chunks3 = mp.chunks3; m.path = SG_PATH_MULTIPASS;
     int lrc;
     switch (P) {
-        case 1: lrc = sg_launch_march2<T, 1>(m, a.nout, st); break;
-        case 2: lrc = sg_launch_march2<T, 2>(m, a.nout, st); break;
-        default: lrc = sg_launch_march2<T, 3>(m, a.nout, st); break;
+        case 1: lrc = sg_launch_march2<T, 1>(m, a.nout, known, st); break;
+        case 2: lrc = sg_launch_march2<T, 2>(m, a.nout, known, st); break;
+        default: lrc = sg_launch_march2<T, 3>(m, a.nout, known, st); break;
     }
     if (lrc != SG_OK) return lrc;
     {
@@ -407,7 +519,7 @@ static int sg_run_march2(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &s
 
 template <typename T>
 int sg_evaluate_adjoint_fast(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &ss, SgAdjointHeader *hdr,
-                             const T *eval, const T *weights, void *scratch, cudaStream_t st)
+                             const T *eval, const T *weights, void *scratch, const SgAdjKnown &known, cudaStream_t st)
 {
     const bool rational = weights != nullptr;
     if (!sg_adjoint_fast_supported(a.nin, a.degree, rational)) return SG_ERR_UNSUPPORTED;
@@ -418,13 +530,18 @@ int sg_evaluate_adjoint_fast(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T
     if (!mp.ok) SG_CUDA(cudaMemsetAsync(cp, 0, (size_t)a.cp_total * a.nout * sizeof(T), st));
     int rc;
     if (mp.ok) {
-        rc = sg_run_march2<T>(cp, a, ss, hdr, eval, mp, ws, st);
-        g_sg_last_variant = "adjoint_march2";
+        const char *variant = "adjoint_march2";
+        rc = sg_run_march2<T>(cp, a, ss, hdr, eval, mp, ws, known, &variant, st);
+        g_sg_last_variant = variant;
     } else {
         rc = sg_run_multipass<T>(cp, a, ss, hdr, eval, weights, ws, SG_PATH_MULTIPASS, st);
         g_sg_last_variant = rational ? "adjoint_passes_rational2d" : "adjoint_passes";
     }
     if (rc != SG_OK) return rc;
+    if (known.planned) {                                               // the plan saw monotone spans: no fallback launch
+        cudaError_t e = cudaPeekAtLastError();
+        return e == cudaSuccess ? SG_OK : (int)e;
+    }
     // non-monotone span indices (decided on device): the reference's atomic scatter
     const unsigned sblocks = (unsigned)std::min<int64_t>(sg_blocks(a.n_total, 256), 148 * 4);   // fallback: fixed small grid
     if (rational)
@@ -437,6 +554,6 @@ int sg_evaluate_adjoint_fast(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T
 }
 
 template int sg_evaluate_adjoint_fast<float>(float *, const SgGridArgs<float> &, const SgSpanStarts<float> &, SgAdjointHeader *,
-                                             const float *, const float *, void *, cudaStream_t);
+                                             const float *, const float *, void *, const SgAdjKnown &, cudaStream_t);
 template int sg_evaluate_adjoint_fast<double>(double *, const SgGridArgs<double> &, const SgSpanStarts<double> &, SgAdjointHeader *,
-                                              const double *, const double *, void *, cudaStream_t);
+                                              const double *, const double *, void *, const SgAdjKnown &, cudaStream_t);

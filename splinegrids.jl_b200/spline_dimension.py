@@ -98,6 +98,7 @@ def _common(sd: SplineDimension):
 
 def set_sample_indices_(sd: SplineDimension) -> None:
     """``set_sample_indices!`` (K1) -- src/utils.jl:19-29."""
+    sd.__dict__["_version"] = sd.__dict__.get("_version", 0) + 1   # invalidates adjoint plans (spline_grid.py)
     kn, n_knots, n = _common(sd)
     with torch.cuda.device(sd.device):
         fn = getattr(_lib.lib(), "sg_span_indices_" + _lib.suffix(sd.dtype))
@@ -108,6 +109,7 @@ def set_sample_indices_(sd: SplineDimension) -> None:
 
 def evaluate_dimension_(sd: SplineDimension) -> None:
     """``evaluate!(::SplineDimension)`` (K2) -- src/spline_dimension.jl:231-242."""
+    sd.__dict__["_version"] = sd.__dict__.get("_version", 0) + 1   # invalidates adjoint plans (spline_grid.py)
     kn, n_knots, n = _common(sd)
     with torch.cuda.device(sd.device):
         fn = getattr(_lib.lib(), "sg_basis_tables_" + _lib.suffix(sd.dtype))
@@ -119,6 +121,7 @@ def evaluate_dimension_(sd: SplineDimension) -> None:
 
 def build_(sd: SplineDimension) -> None:
     """Fused K1+K2 (one launch): span lookup + Cox-de Boor tables."""
+    sd.__dict__["_version"] = sd.__dict__.get("_version", 0) + 1   # invalidates adjoint plans (spline_grid.py)
     kn, n_knots, n = _common(sd)
     with torch.cuda.device(sd.device):
         fn = getattr(_lib.lib(), "sg_dimension_build_" + _lib.suffix(sd.dtype))

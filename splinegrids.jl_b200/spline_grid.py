@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 from .arrays import is_colmajor, jl_ones, jl_zeros, to_device
-from .config import after_launch
+from .config import adjoint_plans, after_launch
 from .control_points import (AbstractControlPoints, DefaultControlPoints, LocallyRefinedControlPoints,
                              evaluate_adjoint_control_points_, evaluate_control_points_, obtain)
 from .spline_dimension import SplineDimension, evaluate_dimension_
@@ -140,7 +140,8 @@ def _prepared_key(kind, grid, der, cp, eval_):
     return (kind, der, cp.data_ptr(), eval_.data_ptr(), cp.shape, cp.stride(), cp.dtype, eval_.shape, eval_.stride(),
             eval_.dtype, 0 if grid.weights is None else grid.weights.data_ptr(),
             tuple(sd.eval.data_ptr() for sd in grid.spline_dimensions),
-            tuple(sd.sample_indices.data_ptr() for sd in grid.spline_dimensions))
+            tuple(sd.sample_indices.data_ptr() for sd in grid.spline_dimensions),
+            tuple(sd.__dict__.get("_version", 0) for sd in grid.spline_dimensions))
 
 
 def _prepared_store(grid, key, value):
@@ -188,23 +189,44 @@ def evaluate_(obj, *, derivative_order: Optional[Sequence[int]] = None, control_
     return None
 
 
-_workspaces = {}
-
-
 def _workspace(grid: SplineGrid) -> torch.Tensor:
-    """Per-(device, size) cached adjoint workspace so the hot loop never allocates."""
+    """Adjoint workspace owned by the grid (its raw pointer is baked into prepared calls and captured CUDA graphs, so
+    its lifetime is the grid's).  One grid must not run evaluate_adjoint! on two streams at the same time."""
     sds = grid.spline_dimensions
     nbytes = int(_lib.lib().sg_evaluate_adjoint_workspace_bytes(
         C.c_int(len(sds)), _lib.i64_array([sd.n_sample_points for sd in sds]),
         _lib.i64_array([sd.n_basis_functions for sd in sds]), C.c_int(grid.Nout),
         _lib.int_array([sd.degree for sd in sds]), C.c_int(grid.eval.element_size()),
         C.c_int(1 if grid.is_nurbs() else 0)))
-    key = (grid.device, nbytes)
-    ws = _workspaces.get(key)
-    if ws is None:
+    ws = grid.__dict__.get("_adjoint_ws")
+    if ws is None or ws.numel() < nbytes or ws.device != grid.device:
         ws = torch.empty(nbytes, dtype=torch.uint8, device=grid.device)
-        _workspaces[key] = ws
+        grid.__dict__["_adjoint_ws"] = ws
     return ws
+
+
+class _AdjointPlan:
+    """Owner of one ``sg_adjoint_plan`` handle (include/splinegrids_b200.h): destroyed with the prepared call."""
+
+    def __init__(self, grid: SplineGrid, der):
+        self.handle = C.c_void_p(0)
+        fn = getattr(_lib.lib(), "sg_adjoint_plan_create_" + _lib.suffix(grid.dtype))
+        with torch.cuda.device(grid.device):
+            _lib.check(fn(C.byref(self.handle), *_grid_call_args(grid, der), C.c_int(1 if grid.is_nurbs() else 0),
+                          _lib.stream_ptr(grid.device)), "sg_adjoint_plan_create")
+
+    def info(self):
+        mono, fused, rows = C.c_int(0), C.c_int(0), C.c_int(0)
+        _lib.check(_lib.lib().sg_adjoint_plan_info(self.handle, C.byref(mono), C.byref(fused), C.byref(rows)), "sg_adjoint_plan_info")
+        return {"monotone": bool(mono.value), "fused_tables_fit": bool(fused.value), "rows2_max": rows.value}
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.lib().sg_adjoint_plan_destroy(self.handle)
+                self.handle = C.c_void_p(0)
+        except Exception:
+            pass
 
 
 def evaluate_adjoint_(obj, *, derivative_order: Optional[Sequence[int]] = None, control_points=None,
@@ -226,23 +248,29 @@ def evaluate_adjoint_(obj, *, derivative_order: Optional[Sequence[int]] = None, 
     eval_ = grid.eval if eval is None else eval
     cp = obtain(control_points)
     # _push = (tag, peer_ptrs, world, rank, k0, np, max_planes[, keep_local]): fused gradient push (distributed.PeerGradientExchange)
-    key = _prepared_key("adj" if _push is None else ("adj_push", _push[0]), grid, der, cp, eval_)
+    key = _prepared_key(("adj", adjoint_plans()) if _push is None else ("adj_push", _push[0], adjoint_plans()), grid, der, cp, eval_)
     prep = grid.__dict__.get("_prepared", {}).get(key)
     if prep is None:
         validate_partial_derivatives(grid.spline_dimensions, der, is_nurbs=grid.is_nurbs())
         cp = _check_arrays(grid, control_points, eval_)
         ws = _workspace(grid)
-        args = (_lib.ptr(cp), *_grid_call_args(grid, der), _lib.ptr(eval_), _lib.ptr(grid.weights), _lib.ptr(ws),
-                C.c_size_t(ws.numel()))
-        if _push is None:
-            fn = getattr(_lib.lib(), "sg_evaluate_adjoint_" + _lib.suffix(grid.dtype))
+        plan = None
+        if adjoint_plans():
+            plan = _AdjointPlan(grid, der)
+            fn = getattr(_lib.lib(), "sg_evaluate_adjoint_planned_" + _lib.suffix(grid.dtype))
+            args = (plan.handle, _lib.ptr(cp), _lib.ptr(eval_), _lib.ptr(grid.weights), _lib.ptr(ws), C.c_size_t(ws.numel()))
+            if _push is None:
+                args = args + (C.c_void_p(0), C.c_int(0), C.c_int(0), C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int(1))
         else:
-            fn = getattr(_lib.lib(), "sg_evaluate_adjoint_push_" + _lib.suffix(grid.dtype))
+            args = (_lib.ptr(cp), *_grid_call_args(grid, der), _lib.ptr(eval_), _lib.ptr(grid.weights), _lib.ptr(ws),
+                    C.c_size_t(ws.numel()))
+            fn = getattr(_lib.lib(), "sg_evaluate_adjoint_" + ("" if _push is None else "push_") + _lib.suffix(grid.dtype))
+        if _push is not None:
             _, peer_ptrs, world, rank, k0, np_, max_planes = _push[:7]
             keep_local = _push[7] if len(_push) > 7 else 1
             args = args + (peer_ptrs, C.c_int(world), C.c_int(rank), C.c_int64(k0), C.c_int64(np_), C.c_int64(max_planes),
                            C.c_int(keep_local))
-        prep = (fn, args, grid.device.index, ws)
+        prep = (fn, args, grid.device.index, ws, plan)
         _prepared_store(grid, key, prep)
     fn, args, dev_index = prep[0], prep[1], prep[2]
     if torch.cuda.current_device() == dev_index:

@@ -204,7 +204,7 @@ MARCH2_CASES = [((20, 11, 9), (3, 3, 3), (128, 400, 20), 1, "Float64", 0, False)
                 ((9, 40, 7), (3, 3, 3), (130, 45, 33), 1, "Float64", 0, False)]      # ~1 sample per span in dim 2, ragged n1
 
 
-@pytest.mark.parametrize("m2f", ["1", "0"], ids=["fused1", "post2"])
+@pytest.mark.parametrize("m2f", ["1", "0"], ids=["fused", "post2"])
 @pytest.mark.parametrize("case,env,variant", [(c, "SG_ADJ_MARCH2", "adjoint_march2") for c in MARCH2_CASES],
                          ids=[f"march2-{c[0]}-{c[1]}" for c in MARCH2_CASES])
 def test_forced_double_march_vs_oracle(S, case, env, variant, m2f, monkeypatch):
@@ -215,7 +215,7 @@ def test_forced_double_march_vs_oracle(S, case, env, variant, m2f, monkeypatch):
     e = np.asfortranarray(rng.random(tuple(n_s) + (nout,)).astype(cp.dtype))
     g = torch.full_like(grid.control_points.obtain(), -3.0)
     monkeypatch.setenv(env, "1")
-    monkeypatch.setenv("SG_ADJ_M2F", m2f)
+    monkeypatch.setenv("SG_ADJ_M2G", m2f)
     S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g)
     assert S.last_variant().startswith(variant)
     gref = oracle_adjoint(grid, e)
@@ -233,7 +233,7 @@ POST2_CASES = [
 ]
 
 
-@pytest.mark.parametrize("m2f", ["1", "0"], ids=["fused1", "post2"])
+@pytest.mark.parametrize("m2f", ["1", "0"], ids=["fused", "post2"])
 @pytest.mark.parametrize("distribution", ["equispaced", "random"])
 @pytest.mark.parametrize("case", POST2_CASES, ids=[f"{c[0]}-{c[1]}-{c[4]}" for c in POST2_CASES])
 def test_double_march_post_kernel_vs_oracle(S, case, distribution, m2f, monkeypatch):
@@ -245,7 +245,7 @@ def test_double_march_post_kernel_vs_oracle(S, case, distribution, m2f, monkeypa
     e = np.asfortranarray(rng.random(tuple(n_s) + (nout,)).astype(cp.dtype))
     g = torch.full_like(grid.control_points.obtain(), -7.0)
     monkeypatch.setenv("SG_ADJ_MARCH2", "1")
-    monkeypatch.setenv("SG_ADJ_M2F", m2f)
+    monkeypatch.setenv("SG_ADJ_M2G", m2f)
     S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g)
     assert S.last_variant().startswith("adjoint_march2")
     gref = oracle_adjoint(grid, e)
@@ -261,6 +261,73 @@ def test_double_march_post_kernel_vs_oracle(S, case, distribution, m2f, monkeypa
         g3 = torch.full_like(g, 1.0)
         S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g3)
         assert rel_err(S.to_numpy(g3), gref) <= _tol(ft), ctas
+
+
+FUSED_CASES = [
+    # n_cp, degree, n_samples, nout, float type, distribution: shapes the fused double march (sg_adjoint_march2g.cuh) takes
+    ((36, 35, 20), (3, 3, 3), (256, 128, 64), 1, "Float64", "equispaced"),     # ~7.8 samples per span in dimension 1
+    ((70, 20, 12), (2, 2, 2), (384, 72, 40), 2, "Float32", "equispaced"),      # Nout 2, Float32, degree 2
+    ((50, 30, 9), (1, 1, 1), (200, 100, 30), 3, "Float64", "equispaced"),      # ragged last column block, degree 1
+    ((40, 23, 21), (5, 3, 3), (200, 70, 64), 1, "Float64", "equispaced"),      # degree 5 in dimension 1
+    ((10, 20, 12), (3, 3, 3), (512, 80, 40), 1, "Float64", "equispaced"),      # 73 samples per span: support = whole block
+    ((67, 20, 12), (3, 3, 3), (128, 72, 40), 1, "Float64", "equispaced"),      # 2 samples per span: 70 control indices per block
+    ((36, 35, 20), (3, 3, 3), (256, 128, 64), 1, "Float64", "random"),         # random sample points (may leave the fused path)
+]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES, ids=[f"{c[0]}-{c[1]}-{c[4]}-{c[5]}" for c in FUSED_CASES])
+def test_fused_double_march_vs_oracle(S, case, monkeypatch):
+    """Planned adjoint of 3-D grids: all three contractions in the march kernel + the halo-sum kernel, against the C
+    oracle; deterministic; same result (up to summation order) as the plain entry point and the unfused pipeline."""
+    from gpu_helpers import make_grid, oracle_adjoint
+    n_cp, deg, n_s, nout, ft, distribution = case
+    grid, cp, w, rng = make_grid(n_cp, deg, n_s, nout, ft, mdo=0, seed=43, distribution=distribution)
+    e = np.asfortranarray(rng.random(tuple(n_s) + (nout,)).astype(cp.dtype))
+    g = torch.full_like(grid.control_points.obtain(), -7.0)
+    monkeypatch.setenv("SG_ADJ_MARCH2", "1")
+    monkeypatch.setenv("SG_ADJ_M2G", "1")                            # opt-in variant
+    S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g)
+    if distribution == "equispaced":
+        assert S.last_variant() == "adjoint_march2_fused"
+    else:
+        assert S.last_variant().startswith("adjoint_march2")
+    gref = oracle_adjoint(grid, e)
+    assert rel_err(S.to_numpy(g), gref) <= _tol(ft)
+    assert max_rel_err(S.to_numpy(g), gref) <= 10 * _tol(ft)
+    g2 = torch.full_like(g, 9.0)
+    S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g2)
+    assert torch.equal(g, g2)                                        # deterministic
+    for ctas in ("1", "100000"):                                     # other chunkings of dimension 3
+        monkeypatch.setenv("SG_ADJ_M2_CTAS", ctas)
+        grid2, _, _, _ = make_grid(n_cp, deg, n_s, nout, ft, mdo=0, seed=43, distribution=distribution)
+        g3 = torch.full_like(g, 1.0)
+        S.evaluate_adjoint_(grid2, eval=S.to_device(e), control_points=g3)
+        assert rel_err(S.to_numpy(g3), gref) <= _tol(ft), ctas
+    monkeypatch.delenv("SG_ADJ_M2_CTAS")
+    S.set_adjoint_plans(False)                                       # plain sg_evaluate_adjoint: decisions on device
+    try:
+        g4 = torch.full_like(g, 2.0)
+        S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g4)
+        assert S.last_variant() == "adjoint_march2"
+        assert rel_err(S.to_numpy(g4), gref) <= _tol(ft)
+    finally:
+        S.set_adjoint_plans(True)
+
+
+def test_adjoint_plan_invalidated_by_dimension_rebuild(S):
+    """A plan captures the inverse sample map; evaluate!(spline_dimension) / set_sample_indices! on new sample points
+    must not leave a stale plan behind (the prepared-call key holds the dimensions' versions)."""
+    from gpu_helpers import make_grid, oracle_adjoint
+    grid, cp, w, rng = make_grid((36, 35, 20), (3, 3, 3), (256, 128, 64), 1, "Float64", mdo=0, seed=47)
+    e = np.asfortranarray(rng.random((256, 128, 64, 1)))
+    g = torch.zeros_like(grid.control_points.obtain())
+    S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g)
+    sd = grid.spline_dimensions[0]
+    sd.sample_points.copy_(torch.sort(torch.rand_like(sd.sample_points)).values)
+    S.set_sample_indices_(sd)
+    S.evaluate_(sd)
+    S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g)
+    assert rel_err(S.to_numpy(g), oracle_adjoint(grid, e)) <= 1e-12
 
 
 def test_evaluate_with_raw_and_reshaped_arrays(S):
