@@ -26,23 +26,6 @@
 #define SG_M2G_EP (128 + 32)      // row pitch of the epilogue buffer: column c lives at c + (c >> 2)
 #define SG_M2G_MAXPL 64           // planes of dimension-3 tables staged at a time
 
-// Weights of dimension 2 and the first sample of each of its knot spans, passed BY VALUE as a kernel parameter (a plan
-// keeps the host copy): they are CTA-uniform, so the compiler reads them through the constant bank into uniform
-// registers (LDCU) and feeds them to DFMA/FFMA as uniform operands -- none of the 80 weight loads per sample plane
-// touches the shared-memory pipe any more (they were half of the kernel's LSU wavefronts), and absent row slots are
-// skipped with uniform predicates.
-#define SG_M2U_B2_BYTES 24576
-#define SG_M2U_STARTS 512
-template <typename T>
-struct SgM2Uni {
-    T b2[SG_M2U_B2_BYTES / sizeof(T)];   // [row of dimension 2][k], k = 0..P
-    int start2[SG_M2U_STARTS];           // span_start of dimension 2, [0 .. c2 + 1]
-    int start3[SG_M2U_STARTS];           // span_start of dimension 3, [0 .. c3 + 1]
-    int span_first3, span_last3;         // first / last span of dimension 3 that holds samples (header values)
-};
-template <typename T>
-struct SgM2UniNone {};
-
 template <typename T>
 struct SgAdj2gArgs {
     const T *X;                 // eval (n1, n2, n3, nout)

@@ -34,7 +34,8 @@ __global__ void __launch_bounds__(128, 5) sg_adj_post2_kernel(T *__restrict__ cp
     const int tid = threadIdx.x;
     const int t = (int)(blockIdx.x % (unsigned)(tiles2 + 1));          // tile of dimension 2 (tiles2 = the last tile's halo rows)
     const int64_t ib = blockIdx.x / (unsigned)(tiles2 + 1);            // block of control indices of dimension 1
-    const int64_t i3 = (int64_t)blockIdx.y + 1;                         // 1-based control index of dimension 3
+    // planes in DESCENDING order: the march kernel wrote the high planes last, they are the ones still in L2
+    const int64_t i3 = (int64_t)(gridDim.y - blockIdx.y);              // 1-based control index of dimension 3
     const int64_t o = blockIdx.z;
     const int64_t i2_0 = (int64_t)t * G2;                               // 0-based control row of slot 0
     if (i2_0 >= c2) return;

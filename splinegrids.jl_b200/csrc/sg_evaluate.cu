@@ -263,7 +263,7 @@ static int sg_adjoint_plan_create_impl(sg_adjoint_plan **out, int nin, const int
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) rc = (int)e;
     }
-    if (rc == SG_OK && p->L.g.ok && p->h.nonmonotone == 0 && p->h.m2g_bad == 0) {
+    if (rc == SG_OK && nin == 3 && !p->rational && p->h.nonmonotone == 0 && degree[1] == degree[2] && degree[1] >= 1 && degree[1] <= 3) {
         // host copy of dimension 2's selected table slice and span starts: kernel parameter of the fused double march
         const int64_t n2 = n_samples[1], c2 = n_cp[1];
         const int P = degree[1];

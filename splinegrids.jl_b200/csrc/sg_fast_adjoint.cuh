@@ -17,6 +17,7 @@
 // denominator (eval is scaled by 1/denom on the fly) and pass B multiplies by w: R' e = w .* B'(e ./ (B w)).
 // Reference semantics: src/adjoint.jl:1-83.
 #pragma once
+#include <type_traits>
 #include "sg_adjoint_generic.cuh"
 #include "sg_common.cuh"
 #include "sg_fast_eval.cuh"
@@ -668,6 +669,43 @@ __device__ __forceinline__ void sg_m2_tma_load_3d_elect(uint32_t dst, const CUte
         "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
         : "memory");
 }
+// L2 policies: the sample array is read exactly once (evict first), the partials are read back by the post kernel right
+// after this kernel (evict last): with a 126 MB L2 a good part of the 135 MB of partials never waits for HBM.
+__device__ __forceinline__ uint64_t sg_l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t sg_l2_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void sg_m2_tma_load_3d_elect_hint(uint32_t dst, const CUtensorMap *tmap, int c0, int c1, int c2, uint32_t bar, uint64_t pol)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "@p cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;\n"
+        "}\n" ::"r"(dst),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(pol)
+        : "memory");
+}
+template <typename T>
+__device__ __forceinline__ void sg_st_hint(T *p, T v, uint64_t pol);
+template <>
+__device__ __forceinline__ void sg_st_hint<double>(double *p, double v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+template <>
+__device__ __forceinline__ void sg_st_hint<float>(float *p, float v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
 // Tensor maps over eval viewed as (n1, n2, n3*nout) with boxes of 128 columns x (1 .. SG_M2_FAST_ROWS) rows x 1 plane: the rows of
 // one knot span of a tile are ONE tensor copy (4 copy instructions per plane instead of ~17 row copies).
 struct SgM2Maps {
@@ -716,14 +754,32 @@ __device__ __forceinline__ void sg_mbar_arrive(uint64_t *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sg_smem_u32(bar)) : "memory");
 }
 
+// Weights of dimension 2 and the first sample of each of its knot spans, passed BY VALUE as a kernel parameter (a plan
+// keeps the host copy): they are CTA-uniform, so the compiler reads them through the constant bank into uniform
+// registers (LDCU) and feeds them to DFMA/FFMA as uniform operands -- none of the 80 weight loads per sample plane
+// touches the shared-memory pipe any more (they were half of the kernel's LSU wavefronts), and absent row slots are
+// skipped with uniform predicates.
+#define SG_M2U_B2_BYTES 24576
+#define SG_M2U_STARTS 512
+template <typename T>
+struct SgM2Uni {
+    T b2[SG_M2U_B2_BYTES / sizeof(T)];   // [row of dimension 2][k], k = 0..P
+    int start2[SG_M2U_STARTS];           // span_start of dimension 2, [0 .. c2 + 1]
+    int start3[SG_M2U_STARTS];           // span_start of dimension 3, [0 .. c3 + 1]
+    int span_first3, span_last3;         // first / last span of dimension 3 that holds samples (header values)
+};
+template <typename T>
+struct SgM2UniNone {};
+
 // Warp-specialised: warps 0-3 (128 threads) consume, warp 4 produces (one elected lane issues the bulk copies).
 // full[st]  : producer -> consumers, completes when the plane's bytes have landed (expect_tx)
 // empty[st] : consumers -> producer, 128 arrivals once every consumer has read the stage
 // No block-wide barrier inside the plane loop; the (CTA-uniform) dimension-3 table rows are staged per piece of
 // MAXPL planes.
-template <typename T, int P, int G2, int RTMAX, int NS, int EXPER = 0>
+template <typename T, int P, int G2, int RTMAX, int NS, bool UW = false>
 __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_constant__ SgAdj2Args<T> a, const __grid_constant__ SgM2Maps maps,
-                                                                   int use_maps)
+                                                                   int use_maps,
+                                                                   const __grid_constant__ typename std::conditional<UW, SgM2Uni<T>, SgM2UniNone<T>>::type uni)
 {
     if (!sg_adj_path_active(a.hdr, a.path)) return;
     constexpr int S = G2 + P;
@@ -737,12 +793,13 @@ __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_
     __shared__ int s3s[MAXPL];
     __shared__ int row0[G2 + 1];
     constexpr int RS5 = SG_M2_FAST_ROWS;                                // row slots per span of the straight-line contraction
-    __shared__ __align__(16) T b2pad[G2 * RS5 * (P + 1)];               // [span g][row q][k], zero for absent rows
+    __shared__ __align__(16) T b2pad[UW ? 1 : G2 * RS5 * (P + 1)];      // [span g][row q][k], zero for absent rows
     __shared__ __align__(8) uint64_t full[NS];
     __shared__ __align__(8) uint64_t empty[NS];
 
     const int tid = threadIdx.x;
-    const bool is_producer = tid >= CW;
+    // the warp index through a shuffle: the role branch is then warp-uniform for the compiler (uniform datapath inside)
+    const bool is_producer = __shfl_sync(0xffffffffu, tid >> 5, 0) >= CW / 32;
     const int64_t j1_0 = (int64_t)blockIdx.x * CW;
     const int64_t j1 = j1_0 + tid;
     const int tile2 = blockIdx.y;
@@ -752,13 +809,24 @@ __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_
     const int ncols = (int)min((int64_t)CW, a.n1 - j1_0);
 
     const int s2_lo = P + 1 + tile2 * G2;
-    if (tid <= G2) row0[tid] = a.start2[(int)min((int64_t)s2_lo + tid, a.c2 + 1)];
+    // rows of the tile's spans: [ur0[g], ur0[g + 1]).  UW: from the kernel parameter (uniform registers), else from memory.
+    int ur0[G2 + 1];
+    if constexpr (UW) {
+#pragma unroll
+        for (int g = 0; g <= G2; ++g) ur0[g] = uni.start2[min(s2_lo + g, (int)a.c2 + 1)];
+    } else {
+        if (tid <= G2) row0[tid] = a.start2[(int)min((int64_t)s2_lo + tid, a.c2 + 1)];
+    }
     if (tid == 0) {
 #pragma unroll
         for (int q = 0; q < NS; ++q) { sg_mbar_init(&full[q], 1); sg_mbar_init(&empty[q], CW / 32); }   // one arrival per consumer warp
     }
     __syncthreads();
-    const int r_first = row0[0], n_rows = row0[G2] - row0[0];
+    if constexpr (!UW) {
+#pragma unroll
+        for (int g = 0; g <= G2; ++g) ur0[g] = row0[g];
+    }
+    const int r_first = ur0[0], n_rows = ur0[G2] - ur0[0];
     // Straight-line contraction of dimension 2 (no data-dependent loops, no predicates): a ring stage holds G2 x RS5
     // fixed row slots, slot (g, q) = q-th row of span g of the tile.  The producer copies every present row into its
     // slot; absent slots are zeroed once here and never written again, and their weights are zero.  Tiles with a span
@@ -766,12 +834,12 @@ __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_
     static_assert(G2 * SG_M2_FAST_ROWS <= RTMAX, "ring stage holds G2 x RS5 row slots");
     bool fastrows = true;
 #pragma unroll
-    for (int g = 0; g < G2; ++g) fastrows = fastrows && row0[g + 1] - row0[g] <= RS5;
+    for (int g = 0; g < G2; ++g) fastrows = fastrows && ur0[g + 1] - ur0[g] <= RS5;
     if (!fastrows) {
         if (tid == 0) a.hdr->m2_skipped = 1;
         return;
     }
-    if (!is_producer) {
+    if (!UW && !is_producer) {
         for (int q = tid; q < G2 * RS5 * (P + 1); q += CW) {
             const int k = q % (P + 1), gq = q / (P + 1), g = gq / RS5, qq = gq % RS5;
             b2pad[q] = qq < row0[g + 1] - row0[g] ? sg_ldg(a.table2 + (row0[g] + qq) + a.n2 * k) : T(0);
@@ -782,11 +850,16 @@ __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_
         }
     }
 
-    const int G3e = sg_m2_chunk_len(a.hdr, P, a.chunks3);
-    const int s3_lo = a.hdr->span_first[2] + c3k * G3e;
-    const int s3_hi = min(s3_lo + G3e, a.hdr->span_last[2] + 1);
+    int sf3, sl3;
+    if constexpr (UW) { sf3 = uni.span_first3; sl3 = uni.span_last3; }
+    else { sf3 = a.hdr->span_first[2]; sl3 = a.hdr->span_last[2]; }
+    const int G3e = max(max(P, 1), (sl3 - sf3 + 1 + a.chunks3 - 1) / a.chunks3);   // == sg_m2_chunk_len
+    const int s3_lo = sf3 + c3k * G3e;
+    const int s3_hi = min(s3_lo + G3e, sl3 + 1);
     if (s3_lo >= s3_hi) return;                                        // block-uniform
-    const int64_t j3_lo = a.start3[s3_lo], j3_hi = a.start3[s3_hi];
+    int64_t j3_lo, j3_hi;
+    if constexpr (UW) { j3_lo = uni.start3[s3_lo]; j3_hi = uni.start3[s3_hi]; }
+    else { j3_lo = a.start3[s3_lo]; j3_hi = a.start3[s3_hi]; }
     const int np_total = (int)(j3_hi - j3_lo);
     const int rows3 = a.G3 + P;
 
@@ -806,10 +879,11 @@ __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_
     T *__restrict__ const ybase = a.Y;
     const unsigned row_bytes = (unsigned)(ncols * sizeof(T));
 
+    const uint64_t pol_last = sg_l2_policy_evict_last();
     auto emit_oldest = [&]() {
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            __stcs(ybase + (yoff + y_slot * s), acc3[s][0]);
+            if (active) sg_st_hint<T>(ybase + (yoff + y_slot * s), acc3[s][0], pol_last);
 #pragma unroll
             for (int k = 0; k < P; ++k) acc3[s][k] = acc3[s][k + 1];
             acc3[s][P] = T(0);
@@ -827,11 +901,12 @@ __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_
             const uint32_t xs_u = sg_smem_u32(xs), full_u = sg_smem_u32(full), empty_u = sg_smem_u32(empty);
             int ra[G2], rn[G2];
 #pragma unroll
-            for (int g = 0; g < G2; ++g) { ra[g] = row0[g] - r_first; rn[g] = row0[g + 1] - row0[g]; }
+            for (int g = 0; g < G2; ++g) { ra[g] = ur0[g] - r_first; rn[g] = ur0[g + 1] - ur0[g]; }
             if (use_maps) {
                 // one tensor copy per knot span: box = 128 columns x rn[g] rows (columns past n1 are zero-filled by the TMA unit)
                 const unsigned stage_tx = (unsigned)(CW * sizeof(T)) * (unsigned)n_rows;
                 const int pl0 = (int)(a.n3 * o + j3_lo);                // first plane of the chunk in the (n1, n2, n3*nout) view
+                const uint64_t pol_first = sg_l2_policy_evict_first();
                 for (int p = 0; p < np_total; ++p) {
                     if (p >= NS) sg_m2_mbar_wait_u(empty_u + (uint32_t)st * 8u, ph ^ 1u);
                     const uint32_t fb = full_u + (uint32_t)st * 8u;
@@ -840,7 +915,7 @@ __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_
 #pragma unroll
                     for (int g = 0; g < G2; ++g)
                         if (rn[g] > 0)                                  // warp-uniform
-                            sg_m2_tma_load_3d_elect(dst + (uint32_t)(g * RS5 * CW * sizeof(T)), &maps.m[rn[g] - 1], (int)j1_0, r_first + ra[g], pl0 + p, fb);
+                            sg_m2_tma_load_3d_elect_hint(dst + (uint32_t)(g * RS5 * CW * sizeof(T)), &maps.m[rn[g] - 1], (int)j1_0, r_first + ra[g], pl0 + p, fb, pol_first);
                     if (++st == NS) { st = 0; ph ^= 1u; }
                 }
                 return;
@@ -885,18 +960,24 @@ __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_
                 for (int g = 0; g < G2; ++g) {
 #pragma unroll
                     for (int q = 0; q < RS5; ++q) {
-                        if (EXPER == 1 && (g > 0 || q > 0)) continue;   // (measurement only: no contraction of dimension 2)
-                        const T x = xst[(g * RS5 + q) * CW];
+                        if constexpr (UW) {
+                            if (q < ur0[g + 1] - ur0[g]) {              // uniform predicate: absent slots cost nothing
+                                const T x = xst[(g * RS5 + q) * CW];
 #pragma unroll
-                        for (int k = 0; k <= P; ++k) T2[g + k] = fma(b2pad[(g * RS5 + q) * (P + 1) + k], x, T2[g + k]);
+                                for (int k = 0; k <= P; ++k) T2[g + k] = fma(uni.b2[(ur0[g] + q) * (P + 1) + k], x, T2[g + k]);
+                            }
+                        } else {
+                            const T x = xst[(g * RS5 + q) * CW];
+#pragma unroll
+                            for (int k = 0; k <= P; ++k) T2[g + k] = fma(b2pad[(g * RS5 + q) * (P + 1) + k], x, T2[g + k]);
+                        }
                     }
                 }
                 __syncwarp();
                 if ((tid & 31) == 0) sg_mbar_arrive(&empty[st]);        // this warp no longer needs the stage
                 if (++st == NS) { st = 0; ph ^= 1u; }
             }
-            if (!active) continue;
-            // ---- march dimension 3
+            // ---- march dimension 3 (columns past n1 carry zeros / garbage that is never stored)
             const int sl = p - p0;
             const int sp = s3s[sl];
             if (cur < sp) {
@@ -911,11 +992,11 @@ __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_
                 for (int k = 0; k <= P; ++k) acc3[q][k] = fma(b[k], T2[q], acc3[q][k]);
         }
     }
-    if (!active) return;
     while (cur < s3_hi) emit_oldest();
+    if (!active) return;
 #pragma unroll
     for (int k = 0; k < P; ++k) {
 #pragma unroll
-        for (int s = 0; s < S; ++s) __stcs(ybase + (yoff + y_slot * s + y_row3 * k), acc3[s][k]);
+        for (int s = 0; s < S; ++s) sg_st_hint<T>(ybase + (yoff + y_slot * s + y_row3 * k), acc3[s][k], pol_last);
     }
 }
