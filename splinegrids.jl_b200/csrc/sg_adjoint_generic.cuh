@@ -20,6 +20,7 @@ struct SgSpanStarts {
     int32_t *bt_lol;         // [nb1][icap]  (first sample of the support relative to the block | number of samples << 16)
     T *bt_w;                 // [nb1][rmcap][icap] gather weights B1[lo + r, i - span + p], zero beyond the support
     int icap, rmcap, nb1;
+    int bw, rfast;           // samples per column block; weights layout: 1 = [block][li][r], 0 = [block][r][li]
 };
 #define SG_GATHER_RMAX 20
 
@@ -36,7 +37,7 @@ __global__ void sg_adjoint_prep_kernel(const __grid_constant__ SgGridArgs<T> a, 
         const int p0 = a.degree[0];
         const int32_t *__restrict__ idx0 = a.index[0];
         for (int jb = blockIdx.x; jb < ss.nb1; jb += gridDim.x) {
-            const int64_t j_lo = (int64_t)jb * 128, j_hi = min(j_lo + 128, n0);
+            const int64_t j_lo = (int64_t)jb * ss.bw, j_hi = min(j_lo + ss.bw, n0);
             __syncthreads();
             if (threadIdx.x == 0) {
                 s_ilo = idx0[j_lo] - p0;
@@ -58,14 +59,15 @@ __global__ void sg_adjoint_prep_kernel(const __grid_constant__ SgGridArgs<T> a, 
                 atomicMax(&s_rm, len);
                 const int len_w = min(len, ss.rmcap);
                 ss.bt_lol[(int64_t)jb * ss.icap + li] = (int32_t)(first - j_lo) | (len_w << 16);
-                T *__restrict__ wp = ss.bt_w + (int64_t)jb * ss.rmcap * ss.icap + li;
+                T *__restrict__ wp = ss.bt_w + (int64_t)jb * ss.rmcap * ss.icap + (ss.rfast ? (int64_t)li * ss.rmcap : (int64_t)li);
+                const int64_t wstride = ss.rfast ? 1 : ss.icap;
                 for (int r = 0; r < ss.rmcap; ++r) {
                     T w = T(0);
                     if (r < len_w) {
                         const int k = min(max((int)(i - idx0[first + r] + p0), 0), p0);   // clamp: garbage-safe
                         w = a.table[0][first + r + n0 * k];
                     }
-                    wp[(int64_t)r * ss.icap] = w;
+                    wp[(int64_t)r * wstride] = w;
                 }
             }
             __syncthreads();

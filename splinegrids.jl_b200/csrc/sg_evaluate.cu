@@ -71,7 +71,7 @@ static SgAdjointLayout sg_adjoint_layout(int nin, const int64_t *n_samples, cons
     L.g_w = off;
     off += sg_align256((size_t)n_cp[0] * SG_GATHER_RMAX * elem_size);
     L.g = SgM2gDims{};
-    if (block_tables) L.g = sg_m2g_dims(nin, n_samples, n_cp, degree, rational);
+    if (block_tables) L.g = sg_m2g_dims(nin, n_samples, n_cp, degree, rational, elem_size);
     if (L.g.ok) {
         L.bt_hdr = off;
         off += sg_align256((size_t)L.g.nb1 * sizeof(SgM2gBlockHdr));
@@ -117,12 +117,12 @@ static void sg_fill_span_starts(SgSpanStarts<T> &ss, const SgAdjointLayout &L, c
     for (int d = 0; d < nin; ++d) ss.start[d] = reinterpret_cast<int32_t *>(prep + L.starts[d]);
     ss.g_lo = reinterpret_cast<int32_t *>(prep + L.g_lo);
     ss.g_w = reinterpret_cast<T *>(prep + L.g_w);
-    ss.bt_hdr = nullptr; ss.bt_lol = nullptr; ss.bt_w = nullptr; ss.icap = ss.rmcap = ss.nb1 = 0;
+    ss.bt_hdr = nullptr; ss.bt_lol = nullptr; ss.bt_w = nullptr; ss.icap = ss.rmcap = ss.nb1 = 0; ss.bw = 128; ss.rfast = 0;
     if (L.g.ok) {
         ss.bt_hdr = reinterpret_cast<SgM2gBlockHdr *>(prep + L.bt_hdr);
         ss.bt_lol = reinterpret_cast<int32_t *>(prep + L.bt_lol);
         ss.bt_w = reinterpret_cast<T *>(prep + L.bt_w);
-        ss.icap = L.g.icap; ss.rmcap = L.g.rmcap; ss.nb1 = L.g.nb1;
+        ss.icap = L.g.icap; ss.rmcap = L.g.rmcap; ss.nb1 = L.g.nb1; ss.bw = L.g.bw; ss.rfast = L.g.rfast;
     }
 }
 

@@ -31,5 +31,7 @@ size_t sg_adjoint_fast_scratch_bytes(int nin, const int64_t *n_samples, const in
 struct SgM2gDims {
     bool ok;
     int icap, rmcap, nb1;
+    int bw;        // samples of dimension 1 per column block (128 for the 3-D double march, 128 * V for the fused 2-D march)
+    int rfast;     // layout of the weights: 1 = [block][li][r] (r fastest, 2-D: lanes walk r), 0 = [block][r][li] (3-D: lanes walk li)
 };
-SgM2gDims sg_m2g_dims(int nin, const int64_t *n_samples, const int64_t *n_cp, const int *degree, bool rational);
+SgM2gDims sg_m2g_dims(int nin, const int64_t *n_samples, const int64_t *n_cp, const int *degree, bool rational, int elem_size);

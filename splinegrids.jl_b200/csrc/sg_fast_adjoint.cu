@@ -2,6 +2,7 @@
 #include <cstdlib>
 
 #include <algorithm>
+#include <cmath>
 #include <type_traits>
 
 #include "sg_evaluate_generic.cuh"
@@ -34,8 +35,29 @@ struct SgAdjPlan {
 
 static size_t sg_al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// Number of chunks of the marching axis of a 2-D grid's first pass from the kernel's RESIDENT capacity (CTAs per SM x SMs):
+// a grid of 1.26 waves runs as long as one of 2 waves, so the chunk count is chosen for full waves, with a mild
+// preference for long chunks (less halo, fewer pipeline fills).  Measured on C4: 23 chunks (368 CTAs, capacity 296) 0.443 ms,
+// 37 chunks (592 CTAs = 2 full waves) 0.332 ms.
+static int64_t sg_pick_nchunks(int64_t nspans, int64_t ctas_per_chunk, int64_t capacity, int P)
+{
+    int64_t best = 1;
+    double best_score = -1.0;
+    for (int64_t nch = 1; nch <= std::min<int64_t>(nspans, 96); ++nch) {
+        const int64_t G = (nspans + nch - 1) / nch, ne = (nspans + G - 1) / G;
+        if (ne != nch) continue;
+        const double ctas = (double)ctas_per_chunk * ne, waves = std::ceil(ctas / capacity);
+        const double score = ctas / (waves * capacity) * (double)G / ((double)G + 0.25 * P);
+        if (score > best_score) { best_score = score; best = nch; }
+    }
+    return best;
+}
+#define SG_ADJ_NCH_MAX 96
+
+// capacity0 > 0 (2-D grids): resident CTAs of the first pass's kernel, ctas_per_chunk0 its CTAs per chunk;
+// worst = true (workspace query): size the first pass's partials for ANY chunk count the run may pick.
 static SgAdjPlan sg_adjoint_pass_plan(int nin, const int64_t *n_samples, const int64_t *n_cp, int nout, const int *degree,
-                                 int elem_size)
+                                      int elem_size, int64_t capacity0 = 0, int64_t ctas_per_chunk0 = 0, bool worst = false)
 {
     SgAdjPlan pl{};
     const int V = elem_size == 4 ? 4 : 2;
@@ -61,12 +83,21 @@ static SgAdjPlan sg_adjoint_pass_plan(int nin, const int64_t *n_samples, const i
         const int64_t threads = ((ps.inner + V - 1) / V) * outer_est;
         int64_t nchunks = 1;
         if (threads < 24576) nchunks = std::min<int64_t>(nspans, (148 * 8 * 128 + threads - 1) / threads);
+        if (nin == 2 && capacity0 > 0 && ctas_per_chunk0 > 0 && sg_env_int("SG_ADJ_WAVES", 1))
+            nchunks = sg_pick_nchunks(nspans, ctas_per_chunk0, capacity0, ps.P);
         const int forced = sg_env_int("SG_ADJ_CHUNKS", 0);
         if (forced > 0) nchunks = std::min<int64_t>(nspans, forced);
         ps.G = (int)((nspans + nchunks - 1) / nchunks);
         ps.nchunks = (int)((nspans + ps.G - 1) / ps.G);
         ps.part_off = off;
-        if (ps.nchunks > 1) off += sg_al256((size_t)ps.inner * (ps.G + ps.P) * ps.nchunks * outer * elem_size);
+        size_t part_elems = ps.nchunks > 1 ? (size_t)ps.inner * (ps.G + ps.P) * ps.nchunks * outer : 0;
+        if (worst && nin == 2) {                                        // any chunk count up to SG_ADJ_NCH_MAX
+            for (int64_t nch = 2; nch <= std::min<int64_t>(nspans, std::max<int64_t>(SG_ADJ_NCH_MAX, forced)); ++nch) {
+                const int64_t G = (nspans + nch - 1) / nch, ne = (nspans + G - 1) / G;
+                part_elems = std::max(part_elems, (size_t)ps.inner * (G + ps.P) * ne * outer);
+            }
+        }
+        if (part_elems > 0) off += sg_al256(part_elems * elem_size);
         ps.out_off = off;
         off += sg_al256((size_t)ps.inner * ps.c_d * outer * elem_size);
         outer *= ps.c_d;
@@ -92,6 +123,14 @@ static void sg_launch_adj_march_nt(const SgAdjPassArgs<T> &pa, int64_t outer, cu
     constexpr int VV = sizeof(T) == 4 ? 4 : 2;
     const bool vec_ok = (pa.inner % VV == 0) && (reinterpret_cast<uintptr_t>(pa.X) % 16 == 0) &&
                         (reinterpret_cast<uintptr_t>(pa.Y) % 16 == 0);
+    if constexpr (!RAT2D) {
+        if (pa.bt_hdr != nullptr) {                                    // fused 2-D march (the caller checked vec_ok)
+            dim3 grid((unsigned)pa.nb1, (unsigned)pa.nchunks, (unsigned)(outer / NT));
+            sg_adj_march_kernel<T, P, VV, NT, false, true><<<grid, 128, 0, st>>>(pa);
+            g_sg_launches.fetch_add(1);
+            return;
+        }
+    }
     if (vec_ok) {
         dim3 grid((unsigned)((pa.inner + 128 * VV - 1) / (128 * VV)), (unsigned)pa.nchunks, (unsigned)(outer / NT));
         sg_adj_march_kernel<T, P, VV, NT, RAT2D><<<grid, 128, 0, st>>>(pa);
@@ -118,6 +157,47 @@ static void sg_launch_adj_march(const SgAdjPassArgs<T> &pa, int64_t outer, int n
     }
 }
 
+// Resident CTAs (all SMs) of the pass-A kernel instantiation a 2-D grid will run: occupancy API, cached per instantiation.
+template <typename T, int P, int NT, bool RAT, bool F1>
+static int64_t sg_adj_march_capacity_inst()
+{
+    static const int64_t cap = [] {
+        constexpr int VV = sizeof(T) == 4 ? 4 : 2;
+        int per_sm = 0, dev = 0, sms = 148;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sg_adj_march_kernel<T, P, VV, NT, RAT, F1>, 128, 0) != cudaSuccess || per_sm < 1) {
+            cudaGetLastError();
+            return (int64_t)0;
+        }
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        return (int64_t)per_sm * sms;
+    }();
+    return cap;
+}
+template <typename T>
+static int64_t sg_adj_march_capacity(int P, int nt, bool rational, bool fused)
+{
+    if (rational) {
+        if (P < 1 || P > 3) return 0;
+#define SG_CAP_RAT(PP)                                                               \
+    switch (nt) {                                                                    \
+        case 4: return sg_adj_march_capacity_inst<T, PP, 4, true, false>();          \
+        case 3: return sg_adj_march_capacity_inst<T, PP, 3, true, false>();          \
+        case 2: return sg_adj_march_capacity_inst<T, PP, 2, true, false>();          \
+        default: return sg_adj_march_capacity_inst<T, PP, 1, true, false>();         \
+    }
+        if (P == 1) { SG_CAP_RAT(1) } else if (P == 2) { SG_CAP_RAT(2) } else { SG_CAP_RAT(3) }
+#undef SG_CAP_RAT
+    }
+    switch (P) {
+        case 1: return fused ? sg_adj_march_capacity_inst<T, 1, 1, false, true>() : sg_adj_march_capacity_inst<T, 1, 1, false, false>();
+        case 2: return fused ? sg_adj_march_capacity_inst<T, 2, 1, false, true>() : sg_adj_march_capacity_inst<T, 2, 1, false, false>();
+        case 3: return fused ? sg_adj_march_capacity_inst<T, 3, 1, false, true>() : sg_adj_march_capacity_inst<T, 3, 1, false, false>();
+        case 4: return fused ? sg_adj_march_capacity_inst<T, 4, 1, false, true>() : sg_adj_march_capacity_inst<T, 4, 1, false, false>();
+        case 5: return fused ? sg_adj_march_capacity_inst<T, 5, 1, false, true>() : sg_adj_march_capacity_inst<T, 5, 1, false, false>();
+        default: return 0;
+    }
+}
+
 // ---- one generic pass A (+ chunk combine) ---------------------------------------------------------
 template <typename T>
 static void sg_run_pass_a(const SgAdjPass &ps, SgAdjPassArgs<T> &pa, T *out, T *part, bool rat_here, int path,
@@ -139,7 +219,7 @@ static void sg_run_pass_a(const SgAdjPass &ps, SgAdjPassArgs<T> &pa, T *out, T *
             default: sg_launch_adj_march<T, 5, false>(pa, ps.outer, nt, st); break;
         }
     }
-    if (ps.nchunks > 1) {
+    if (ps.nchunks > 1 && pa.bt_hdr == nullptr) {
         constexpr int VC = sizeof(T) == 4 ? 4 : 2;
         const bool vec_ok = (ps.inner % VC == 0);
         dim3 cgrid((unsigned)((ps.inner + 128 * VC - 1) / (128 * VC)), (unsigned)((ps.c_d + SG_COMBINE_ROWS - 1) / SG_COMBINE_ROWS), (unsigned)ps.outer);
@@ -152,10 +232,46 @@ static void sg_run_pass_a(const SgAdjPass &ps, SgAdjPassArgs<T> &pa, T *out, T *
 // ---- multi-pass pipeline ---------------------------------------------------------------------------
 template <typename T>
 static int sg_run_multipass(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &ss, SgAdjointHeader *hdr, const T *eval,
-                            const T *weights, char *ws, int path, cudaStream_t st)
+                            const T *weights, char *ws, int path, const SgAdjKnown &known, const char **variant, cudaStream_t st)
 {
     const bool rational = weights != nullptr;
-    const SgAdjPlan pl = sg_adjoint_pass_plan(a.nin, a.n_samples, a.n_cp, a.nout, a.degree, (int)sizeof(T));
+    int64_t capacity0 = 0, cpc0 = 0;
+    if (a.nin == 2) {                                                  // full waves for the pass that reads the sample array
+        constexpr int VQ = sizeof(T) == 4 ? 4 : 2;
+        const bool fused = known.planned && known.fused_ok && ss.bt_hdr != nullptr && !rational;
+        const int nt = (rational && a.nout <= 4) ? a.nout : 1;
+        capacity0 = sg_adj_march_capacity<T>(a.degree[1], nt, rational, fused);
+        cpc0 = ((a.n_samples[0] + 128 * VQ - 1) / (128 * VQ)) * (a.nout / nt);
+    }
+    const SgAdjPlan pl = sg_adjoint_pass_plan(a.nin, a.n_samples, a.n_cp, a.nout, a.degree, (int)sizeof(T), capacity0, cpc0);
+    {
+        // fused 2-D march (planned calls): dimension 2 marched per column, dimension 1 contracted in the kernel's epilogue
+        constexpr int VV = sizeof(T) == 4 ? 4 : 2;
+        const SgAdjPass &ps = pl.pass[0];
+        T *part = reinterpret_cast<T *>(ws + (ps.nchunks > 1 ? ps.part_off : ps.out_off));
+        const bool nt_ok = !rational || a.nout <= 4;                  // rational: all channels of a thread share the denominators
+        // (rational grids keep the multi-pass pipeline: their fused kernel needs 242 registers and measured slower)
+        if (a.nin == 2 && !rational && known.planned && known.fused_ok && ss.bt_hdr != nullptr && ss.rfast == 1 && ss.bw == 128 * VV && nt_ok &&
+            a.n_samples[0] % VV == 0 && reinterpret_cast<uintptr_t>(eval) % 16 == 0 && ps.outer <= 65535 && ps.nchunks <= 65535) {
+            SgAdjPassArgs<T> pa{};
+            pa.X = eval; pa.Y = part; pa.table = a.table[1]; pa.index = a.index[1]; pa.span_start = ss.start[1];
+            pa.hdr = hdr; pa.inner = ps.inner; pa.n_d = ps.n_d; pa.c_d = ps.c_d; pa.G = ps.G; pa.nchunks = ps.nchunks;
+            pa.path = path; pa.dim = 1; pa.last_dim = -1; pa.restrict_spans = 1;
+            pa.bt_hdr = ss.bt_hdr; pa.bt_lol = ss.bt_lol; pa.bt_w = ss.bt_w; pa.icap = ss.icap; pa.rmcap = ss.rmcap; pa.nb1 = ss.nb1;
+            if (rational) { pa.weights = weights; pa.table1 = a.table[0]; pa.index1 = a.index[0]; pa.c1 = a.n_cp[0]; }
+            sg_run_pass_a<T>(ps, pa, part, part, rational, path, hdr, st);
+            dim3 cgrid(sg_blocks(a.n_cp[0], 128), (unsigned)a.n_cp[1], (unsigned)a.nout);
+            if (rational)
+                sg_adj_combine_f2d_kernel<T, true><<<cgrid, 128, 0, st>>>(cp, part, ss.g_lo, ss.bt_hdr, hdr, weights, a.n_cp[0], a.n_cp[1], ps.G,
+                                                                          ps.nchunks, ps.P, ss.icap, ss.nb1, ss.bw);
+            else
+                sg_adj_combine_f2d_kernel<T, false><<<cgrid, 128, 0, st>>>(cp, part, ss.g_lo, ss.bt_hdr, hdr, weights, a.n_cp[0], a.n_cp[1], ps.G,
+                                                                           ps.nchunks, ps.P, ss.icap, ss.nb1, ss.bw);
+            g_sg_launches.fetch_add(1);
+            *variant = rational ? "adjoint_fused2d_rational" : "adjoint_fused2d";
+            return SG_OK;
+        }
+    }
     for (int k = 0; k < pl.npassA; ++k) {
         const SgAdjPass &ps = pl.pass[k];
         if (ps.outer > 65535 || ps.nchunks > 65535 || (ps.nchunks > 1 && ps.c_d > 65535)) return SG_ERR_UNSUPPORTED;
@@ -270,7 +386,7 @@ static SgMarch2Plan sg_adjoint_march2_plan(int nin, const int64_t *n_samples, co
     off += sg_al256((size_t)n_samples[0] * (mp.G2 + P) * mp.tiles2 * (mp.G3 + P) * mp.chunks3 * nout * elem_size);
     mp.r_off = off;                                                     // (no intermediate array any more: the post kernel reads the partials)
     mp.bytes = mp.bytes_unfused = off;
-    mp.g = sg_m2g_dims(nin, n_samples, n_cp, degree, rational);
+    mp.g = sg_m2g_dims(nin, n_samples, n_cp, degree, rational, elem_size);
     if (mp.g.ok) {
         const double elems = (double)mp.g.icap * (mp.G2 + P) * mp.tiles2 * (mp.G3 + P) * mp.chunks3 * mp.g.nb1 * nout;
         if (elems < 4.0e9) mp.bytes = std::max(mp.bytes, sg_al256((size_t)elems * elem_size));
@@ -283,30 +399,49 @@ static SgMarch2Plan sg_adjoint_march2_plan(int nin, const int64_t *n_samples, co
 // Fused double march: eligibility and table sizes from the shape alone (the prep kernel checks the data on device).
 // Worth it when dimension 1 has at least ~2 samples per knot span (a block of 128 columns then leaves <= ~70 control
 // indices); icap / rmcap leave a factor 2 of slack over equispaced samples.
-SgM2gDims sg_m2g_dims(int nin, const int64_t *n_samples, const int64_t *n_cp, const int *degree, bool rational)
+SgM2gDims sg_m2g_dims(int nin, const int64_t *n_samples, const int64_t *n_cp, const int *degree, bool rational, int elem_size)
 {
     SgM2gDims g{};
     g.ok = false;
-    if (rational || nin != 3 || sg_env_int("SG_ADJ_M2G", 0) == 0) return g;   // opt-in (SG_ADJ_M2G=1): measured slower than the unfused pipeline, see DESIGN.md
-    const int P = degree[1];
-    if (degree[2] != P || P < 1 || P > 3 || degree[0] < 1 || degree[0] > 5) return g;
     const int64_t n1 = n_samples[0], nsp1 = n_cp[0] - degree[0];
-    if (n1 < 128 || n1 < 2 * nsp1) return g;
-    const int64_t est_spans = (128 * nsp1 + n1 - 1) / n1;
+    if (nin == 2) {
+        // fused 2-D march (sg_adj_march_kernel<.., F1 = true>): a column block is the 128 * V columns of one CTA
+        if (sg_env_int("SG_ADJ_F2D", 1) == 0 || !sg_adjoint_fast_supported(nin, degree, rational)) return g;
+        const int V = elem_size == 4 ? 4 : 2;
+        g.bw = 128 * V;
+        g.rfast = 1;
+        if (n1 % V != 0 || n1 < g.bw || n1 < 2 * nsp1) return g;
+        // the epilogue runs once per knot span of dimension 2 and costs ~ one warp pass per control index of the block:
+        // worth it when a block touches few control indices compared with the rows between two emissions
+        // (C2: 6 indices / 67 rows -> 0.078 -> 0.056 ms; C5-scaled: 34 / 17 -> slower than the multi-pass pipeline)
+        const double est_ni = (double)g.bw * nsp1 / n1 + degree[0];
+        const double rows_per_span2 = (double)n_samples[1] / (double)std::max<int64_t>(1, n_cp[1] - degree[1]);
+        if (sg_env_int("SG_ADJ_F2D", 1) != 2 && est_ni > 0.5 * rows_per_span2) return g;
+    } else if (nin == 3) {
+        // opt-in (SG_ADJ_M2G=1): measured slower than the unfused pipeline, see DESIGN.md
+        if (rational || sg_env_int("SG_ADJ_M2G", 0) == 0) return g;
+        const int P = degree[1];
+        if (degree[2] != P || P < 1 || P > 3 || degree[0] < 1 || degree[0] > 5) return g;
+        g.bw = 128;
+        g.rfast = 0;
+        if (n1 < 128 || n1 < 2 * nsp1) return g;
+    } else {
+        return g;
+    }
+    const int64_t est_spans = (g.bw * nsp1 + n1 - 1) / n1;
     g.icap = (int)std::min<int64_t>(((2 * est_spans + degree[0] + 2 + 7) / 8) * 8, 136);
-    g.rmcap = (int)std::min<int64_t>((degree[0] + 1) * ((2 * n1 + nsp1 - 1) / nsp1) + 2, 128);
-    g.nb1 = (int)((n1 + 127) / 128);
+    g.rmcap = (int)std::min<int64_t>((degree[0] + 1) * ((2 * n1 + nsp1 - 1) / nsp1) + 2, g.bw);
+    g.nb1 = (int)((n1 + g.bw - 1) / g.bw);
     if ((int64_t)g.nb1 * g.rmcap * g.icap > (int64_t)1 << 26) return g;
     g.ok = true;
     return g;
 }
 
-
 size_t sg_adjoint_fast_scratch_bytes(int nin, const int64_t *n_samples, const int64_t *n_cp, int nout, const int *degree,
                                      int elem_size)
 {
     if (!sg_adjoint_fast_supported(nin, degree, false)) return 0;
-    const size_t a = sg_adjoint_pass_plan(nin, n_samples, n_cp, nout, degree, elem_size).bytes;
+    const size_t a = sg_adjoint_pass_plan(nin, n_samples, n_cp, nout, degree, elem_size, 0, 0, true).bytes;
     const SgMarch2Plan mp = sg_adjoint_march2_plan(nin, n_samples, n_cp, nout, degree, elem_size, false);
     // the pipelines never run together: they share the scratch
     return std::max(a, mp.ok ? mp.bytes : (size_t)0);
@@ -538,8 +673,9 @@ int sg_evaluate_adjoint_fast(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T
         rc = sg_run_march2<T>(cp, a, ss, hdr, eval, mp, ws, known, &variant, st);
         g_sg_last_variant = variant;
     } else {
-        rc = sg_run_multipass<T>(cp, a, ss, hdr, eval, weights, ws, SG_PATH_MULTIPASS, st);
-        g_sg_last_variant = rational ? "adjoint_passes_rational2d" : "adjoint_passes";
+        const char *variant = rational ? "adjoint_passes_rational2d" : "adjoint_passes";
+        rc = sg_run_multipass<T>(cp, a, ss, hdr, eval, weights, ws, SG_PATH_MULTIPASS, known, &variant, st);
+        g_sg_last_variant = variant;
     }
     if (rc != SG_OK) return rc;
     if (known.planned) {                                               // the plan saw monotone spans: no fallback launch

@@ -64,6 +64,11 @@ struct SgAdjPassArgs {
     int last_dim;               // -1: no skipping
     int last_P;
     int64_t last_div, last_c;
+    // fused 2-D march (F1): column-block tables of dimension 1 (prep kernel), weights [block][li][r]
+    const SgM2gBlockHdr *bt_hdr;
+    const int32_t *bt_lol;
+    const T *bt_w;
+    int icap, rmcap, nb1;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -83,17 +88,29 @@ __device__ __forceinline__ void sg_load_vec(const T *__restrict__ p, T (&x)[V])
     for (int v = 0; v < V; ++v) x[v] = pq[v];
 }
 
-template <typename T, int P, int V, int NT, bool RAT2D>
+// F1 (2-D grids, planned calls): the kernel ALSO contracts dimension 1.  Whenever a control row of dimension 2 is finished
+// (once per knot span, i.e. every n2 / spans rows -- rare), the CTA parks the row's 128 * V values per channel in shared
+// memory and gathers the NI control indices its column block touches: one warp per output (li, channel), the lanes walk
+// the support (coalesced weights from the per-block table, conflict-free shared loads), a shuffle tree finishes the sum.
+// The partials then hold NI values per column block instead of 128 * V: the (n1, c2) intermediate, the chunk-combine
+// kernel and the first-dimension kernel of the multi-pass pipeline disappear (sg_adj_combine_f2d_kernel sums the halos).
+template <typename T, int P, int V, int NT, bool RAT2D, bool F1 = false>
 __global__ void __launch_bounds__(128) sg_adj_march_kernel(const __grid_constant__ SgAdjPassArgs<T> a)
 {
     if (!sg_adj_path_active(a.hdr, a.path)) return;
     __shared__ __align__(16) T bs[SG_ADJ_PIECE * (P + 1)];
     __shared__ int ss[SG_ADJ_PIECE];
+    constexpr int BW = 128 * V;                                         // columns per CTA (F1: one column block)
+    __shared__ __align__(16) T Es[F1 ? NT * BW : 1];
+    __shared__ int lol_s[F1 ? 136 : 1];
     constexpr int E = 1;
     constexpr int WD = P + 1 + E;
     constexpr int U = NT >= 2 ? 4 : 8;                                 // steps whose loads are issued together
 
-    const int64_t q0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
+    int64_t q0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
+    // F1: every thread takes part in the epilogue's barriers; a thread past the end re-reads the last columns (its
+    // values are parked at positions no control index of the block reads)
+    if (F1) q0 = min(q0, a.inner - V);
     const int c = blockIdx.y;
     const int64_t r = (int64_t)blockIdx.z * NT;                       // first of this thread's NT outer channels
     if (!sg_adj_row_in_support(a.hdr, a.last_dim, a.last_P, a.last_div, a.last_c, r)) return;   // block-uniform
@@ -104,12 +121,19 @@ __global__ void __launch_bounds__(128) sg_adj_march_kernel(const __grid_constant
     const int s_hi = a.restrict_spans ? min(s_hi0, a.hdr->span_last[a.dim] + 1) : s_hi0;
     if (s_lo >= s_hi) return;                                          // block-uniform
     const int64_t j_lo = a.span_start[s_lo], j_hi = a.span_start[s_hi];
-    bool active = q0 < a.inner;
+    bool active = F1 || q0 < a.inner;
     const int rows = a.G + P;
     const int64_t inner = a.inner;
 
     const T *__restrict__ xp = a.X + q0 + inner * (j_lo + a.n_d * r);
     T *__restrict__ yp = a.Y + q0 + inner * ((int64_t)rows * (c + (int64_t)a.nchunks * r) + (s_lo - s_lo0));   // oldest live row
+    // F1: partials [li][row][chunk][block][channel]
+    int f_ni = 0;
+    int64_t f_row = s_lo - s_lo0;
+    if (F1) {
+        f_ni = a.bt_hdr[blockIdx.x].ni;
+        for (int q = threadIdx.x; q < f_ni; q += blockDim.x) lol_s[q] = sg_ldg(a.bt_lol + (int64_t)blockIdx.x * a.icap + q);
+    }
     const int64_t x_ch = inner * a.n_d;                                // channel strides
     const int64_t y_ch = inner * (int64_t)rows * a.nchunks;
 
@@ -166,12 +190,21 @@ __global__ void __launch_bounds__(128) sg_adj_march_kernel(const __grid_constant
 
     // write the oldest live row (complete, or chunk-partial) and slide the window by one span
     auto emit_oldest = [&]() {
+        if (F1) __syncthreads();                                        // the previous row's gather is over
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
             T o[V];
 #pragma unroll
             for (int v = 0; v < V; ++v) o[v] = acc[t][v][0];
-            sg_store_vec<T, V>(yp + y_ch * t, o, true, V);
+            if (F1) {
+                typename SgVecT<T, V>::type pk;
+                T *pq = reinterpret_cast<T *>(&pk);
+#pragma unroll
+                for (int v = 0; v < V; ++v) pq[v] = o[v];
+                *reinterpret_cast<typename SgVecT<T, V>::type *>(Es + t * BW + threadIdx.x * V) = pk;
+            } else {
+                sg_store_vec<T, V>(yp + y_ch * t, o, true, V);
+            }
 #pragma unroll
             for (int v = 0; v < V; ++v) {
 #pragma unroll
@@ -181,6 +214,25 @@ __global__ void __launch_bounds__(128) sg_adj_march_kernel(const __grid_constant
         }
         yp += inner;
         ++cur;
+        if (F1) {
+            __syncthreads();
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            const T *__restrict__ wblk = a.bt_w + (int64_t)blockIdx.x * a.rmcap * a.icap;
+            for (int out = warp; out < f_ni * NT; out += 4) {           // one warp per output (li, channel)
+                const int t = out / f_ni, li = out - t * f_ni;
+                const int ll = lol_s[li];
+                const int lo = ll & 0xffff, len = ll >> 16;
+                const T *__restrict__ wp = wblk + (int64_t)li * a.rmcap;
+                const T *__restrict__ ep = Es + t * BW + lo;
+                T sacc = T(0);
+                for (int rr = lane; rr < len; rr += 32) sacc = fma(sg_ldg(wp + rr), ep[rr], sacc);
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, off);
+                if (lane == 0)
+                    a.Y[li + (int64_t)a.icap * (f_row + (int64_t)rows * (c + (int64_t)a.nchunks * ((int64_t)blockIdx.x + (int64_t)a.nb1 * (r + t))))] = sacc;
+            }
+            ++f_row;
+        }
         if (RAT2D && cur <= (int)a.c_d) {
             T o[V];
             wrow((int64_t)cur - 1, o);
@@ -254,6 +306,10 @@ __global__ void __launch_bounds__(128) sg_adj_march_kernel(const __grid_constant
     }
     if (!active) return;
     // flush: finish the chunk's spans, then the P still-live rows
+    if (F1) {
+        while (cur < s_hi + P) emit_oldest();
+        return;
+    }
     while (cur < s_hi) emit_oldest();
 #pragma unroll
     for (int t = 0; t < NT; ++t)
@@ -315,6 +371,46 @@ __global__ void __launch_bounds__(128) sg_adj_combine_kernel(T *__restrict__ Y, 
         }
         sg_store_vec<T, V>(Y + q0 + inner * ((i - 1) + c_d * r), acc, vec, nv);
     }
+}
+
+// Halo sum of the fused 2-D march: cp[i1, i2, o] = (w[i1, i2]) * sum over the chunks of dimension 2 that hold row i2 and the
+// column blocks that hold i1 of the partials; writes every control point (zeros outside the support).
+template <typename T, bool RATIONAL>
+__global__ void __launch_bounds__(128) sg_adj_combine_f2d_kernel(T *__restrict__ cp, const T *__restrict__ Pp, const int32_t *__restrict__ g_lo,
+                                                                 const SgM2gBlockHdr *__restrict__ bt_hdr, const SgAdjointHeader *hdr,
+                                                                 const T *__restrict__ weights, int64_t c1, int64_t c2, int G, int nchunks, int P,
+                                                                 int icap, int nb1, int bw)
+{
+    const int64_t i1 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // 0-based
+    if (i1 >= c1) return;
+    const int64_t i = (int64_t)blockIdx.y + 1;                          // 1-based control row of dimension 2
+    const int64_t o = blockIdx.z;
+    const int2 gl = *reinterpret_cast<const int2 *>(g_lo + 2 * i1);
+    const int sf = hdr->span_first[1], sl = hdr->span_last[1];
+    const int rows = G + P;
+    T acc = T(0);
+    if (hdr->nonmonotone == 0 && gl.y > 0 && i >= sf - P && i <= sl) {
+        int64_t c_hi = (i - 1) / G;
+        if (c_hi > nchunks - 1) c_hi = nchunks - 1;
+        int64_t c_lo = (i - P - 1 >= 0) ? (i - P - 1) / G : 0;
+        if (c_lo > 0 && (c_lo - 1) * G + G + P >= i) --c_lo;
+        const int jb_a = gl.x / bw, jb_b = min((gl.x + gl.y - 1) / bw, nb1 - 1);
+        for (int64_t c = c_lo; c <= c_hi; ++c) {
+            const int64_t local = i - (c * G + 1);
+            if (local < 0 || local >= rows) continue;
+            // rows a chunk really wrote: spans [max(s_lo0, sf), min(s_hi0, sl+1)) -> control rows [lo-P, hi-1]
+            const int64_t cs_lo = max((int64_t)(P + 1 + c * G), (int64_t)sf);
+            const int64_t cs_hi = min(min((int64_t)(P + 1 + c * G + G), c2 + 1), (int64_t)sl + 1);
+            if (cs_lo >= cs_hi || i < cs_lo - P || i > cs_hi - 1) continue;
+            for (int jb = jb_a; jb <= jb_b; ++jb) {
+                const int li = (int)(i1 + 1) - bt_hdr[jb].i1_lo;
+                if (li < 0 || li >= icap) continue;
+                acc += __ldcs(Pp + li + (int64_t)icap * (local + (int64_t)rows * (c + (int64_t)nchunks * (jb + (int64_t)nb1 * o))));
+            }
+        }
+    }
+    const int64_t lin = i1 + c1 * ((i - 1) + c2 * o);
+    cp[lin] = RATIONAL ? acc * sg_ldg(weights + i1 + c1 * (i - 1)) : acc;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -314,6 +314,49 @@ def test_fused_double_march_vs_oracle(S, case, monkeypatch):
         S.set_adjoint_plans(True)
 
 
+F2D_CASES = [
+    # n_cp, degree, n_samples, nout, float type, nurbs, distribution: 2-D shapes the fused march (F1) takes
+    ((20, 12), (3, 3), (1024, 200), 3, "Float32", False, "equispaced"),
+    ((20, 12), (2, 3), (512, 90), 2, "Float64", False, "equispaced"),        # mixed degrees
+    ((9, 40), (3, 2), (768, 70), 1, "Float64", False, "equispaced"),         # 128 samples per span of dimension 1
+    ((30, 10), (3, 3), (600, 64), 2, "Float32", False, "equispaced"),        # ragged last column block
+    ((24, 18), (3, 3), (1024, 160), 3, "Float32", True, "equispaced"),       # rational (NURBS extension)
+    ((24, 18), (2, 2), (512, 100), 2, "Float64", True, "equispaced"),
+    ((40, 12), (3, 3), (1024, 200), 3, "Float32", False, "random"),          # random knots
+    ((200, 9), (1, 1), (512, 40), 4, "Float64", False, "equispaced"),        # 2.6 samples per span: 100+ control indices per block
+]
+
+
+@pytest.mark.parametrize("case", F2D_CASES, ids=[f"{c[0]}-{c[1]}-{c[4]}{'-nurbs' if c[5] else ''}-{c[6]}" for c in F2D_CASES])
+def test_fused_2d_march_vs_oracle(S, case, monkeypatch):
+    """Planned adjoint of 2-D grids: dimension 2 marched per sample column and dimension 1 contracted in the same kernel
+    (sg_adj_march_kernel<F1>) + halo-sum kernel, against the C oracle; deterministic; slab of a sharded grid."""
+    from gpu_helpers import make_grid, oracle_adjoint
+    n_cp, deg, n_s, nout, ft, nurbs, distribution = case
+    grid, cp, w, rng = make_grid(n_cp, deg, n_s, nout, ft, mdo=0, nurbs=nurbs, seed=53, distribution=distribution)
+    e = np.asfortranarray(rng.random(tuple(n_s) + (nout,)).astype(cp.dtype))
+    g = torch.full_like(grid.control_points.obtain(), -7.0)
+    monkeypatch.setenv("SG_ADJ_F2D", "2")                            # also where the cost heuristic would decline
+    S.set_kernel_policy(2)
+    try:
+        S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g, allow_nurbs=nurbs)
+        assert S.last_variant() == ("adjoint_passes_rational2d" if nurbs else "adjoint_fused2d")   # (rational: multi-pass)
+        gref = oracle_adjoint(grid, e, None, w)
+        assert rel_err(S.to_numpy(g), gref) <= _tol(ft)
+        assert max_rel_err(S.to_numpy(g), gref) <= 10 * _tol(ft)
+        g2 = torch.full_like(g, 9.0)
+        S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g2, allow_nurbs=nurbs)
+        assert torch.equal(g, g2)
+        S.set_adjoint_plans(False)                                   # plain entry point: multi-pass pipeline
+        g3 = torch.full_like(g, 2.0)
+        S.evaluate_adjoint_(grid, eval=S.to_device(e), control_points=g3, allow_nurbs=nurbs)
+        assert S.last_variant().startswith("adjoint_passes")
+        assert rel_err(S.to_numpy(g3), gref) <= _tol(ft)
+    finally:
+        S.set_adjoint_plans(True)
+        S.set_kernel_policy(0)
+
+
 def test_adjoint_plan_invalidated_by_dimension_rebuild(S):
     """A plan captures the inverse sample map; evaluate!(spline_dimension) / set_sample_indices! on new sample points
     must not leave a stale plan behind (the prepared-call key holds the dimensions' versions)."""
