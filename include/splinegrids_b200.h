@@ -125,6 +125,18 @@ int sg_evaluate_f64(double *eval, int nin, const int64_t *n_samples, const int64
                     const int *mdo, const int *der, const double *cp, const double *weights_or_null,
                     void *stream);
 
+/* ---- K3 for several derivative orders in one call (row f1 of the scope table): what the reference's callers do with
+ * back-to-back evaluate! calls (docs/src/examples_optics.md:189-191: u, d1 u, d2 u; docs/src/examples_pde.md:69-72).
+ * evals: HOST array of n_der device pointers, each (n_1..n_D, Nout); ders: HOST array n_der x nin (tuple q = ders[q*nin ..]).
+ * 2-D grids of uniform degree 1..3 with 2..4 tuples run ONE fused kernel (control points and span bookkeeping shared by
+ * the tuples); every other case runs one launch per tuple inside this call.  Results are those of n_der sg_evaluate calls. */
+int sg_evaluate_multi_f32(float *const *evals, int n_der, const int *ders, int nin, const int64_t *n_samples,
+                          const int64_t *n_cp, int nout, const float *const *tables, const int32_t *const *indices,
+                          const int *degree, const int *mdo, const float *cp, const float *weights_or_null, void *stream);
+int sg_evaluate_multi_f64(double *const *evals, int n_der, const int *ders, int nin, const int64_t *n_samples,
+                          const int64_t *n_cp, int nout, const double *const *tables, const int32_t *const *indices,
+                          const int *degree, const int *mdo, const double *cp, const double *weights_or_null, void *stream);
+
 /* ---- K4 spline_eval_adjoint_kernel -- src/adjoint.jl:1-40, launcher evaluate_adjoint! :52-83
  * cp[i,o] = sum_{J : i in window(J)} prod_d B_d[..] * eval[J,o]; the callee zero-fills cp first
  * (src/adjoint.jl:61).  No global atomics when the per-dimension span indices are non-decreasing

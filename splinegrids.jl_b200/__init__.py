@@ -22,12 +22,12 @@ from .refinement import (add_default_local_refinement, boehm_refinement_matrix, 
                          insert_knot, refine)
 from .refinement_matrix import (RefinementMatrix, mult_, mult_adjoint_, refinement_matrix_from_dense, rmeye)
 from .spline_dimension import SplineDimension, build_, decompress, set_sample_indices_
-from .spline_grid import NURBSGrid, SplineGrid, evaluate_, evaluate_adjoint_
+from .spline_grid import NURBSGrid, SplineGrid, evaluate_, evaluate_adjoint_, evaluate_multi_
 from .validation import SplineGridsError
 
 __all__ = [
     "SplineDimension", "SplineGrid", "NURBSGrid", "KnotVector", "RefinementMatrix", "DefaultControlPoints",
-    "LocallyRefinedControlPoints", "LocalRefinement", "evaluate_", "evaluate_adjoint_", "mult_", "mult_adjoint_",
+    "LocallyRefinedControlPoints", "LocalRefinement", "evaluate_", "evaluate_adjoint_", "evaluate_multi_", "mult_", "mult_adjoint_",
     "rmeye", "refinement_matrix_from_dense", "decompress", "set_sample_indices_", "build_", "insert_knot", "refine",
     "add_default_local_refinement", "activate_local_refinement_", "activate_local_control_point_range_",
     "deactivate_overwritten_control_points_", "error_informed_local_refinement_", "get_n_control_points", "obtain",

@@ -7,6 +7,7 @@
 #include "sg_adjoint_generic.cuh"
 #include "sg_evaluate_generic.cuh"
 #include "sg_fast.cuh"
+#include "sg_eval_multi.cuh"
 
 static inline size_t sg_align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -35,6 +36,37 @@ static int sg_evaluate_impl(T *eval, int nin, const int64_t *n_samples, const in
         sg_evaluate_generic_kernel<T, false><<<blocks, threads, 0, st>>>(eval, a, cp, weights);
     g_sg_last_variant = "evaluate_generic";
     SG_AFTER_LAUNCH();
+    return SG_OK;
+}
+
+// K3 for several derivative orders: one fused launch where a multi kernel exists, else one launch per tuple
+template <typename T>
+static int sg_evaluate_multi_impl(T *const *evals, int n_der, const int *ders, int nin, const int64_t *n_samples, const int64_t *n_cp,
+                                  int nout, const T *const *tables, const int32_t *const *indices, const int *degree, const int *mdo,
+                                  const T *cp, const T *weights, void *stream)
+{
+    SG_CHECK_ARG(evals && ders && n_der >= 1 && cp);
+    for (int q = 0; q < n_der; ++q) SG_CHECK_ARG(evals[q] != nullptr);
+    cudaStream_t st = sg_stream(stream);
+    if (!weights && n_der >= 2 && n_der <= SG_MULTI_MAX && nin == 2) {
+        SgMultiArgs<T> m{};
+        SgGridArgs<T> a{};
+        int rc = SG_OK;
+        for (int q = 0; q < n_der && rc == SG_OK; ++q) {
+            SgGridArgs<T> aq;
+            rc = sg_fill_grid_args(aq, nin, n_samples, n_cp, nout, tables, indices, degree, mdo, ders + (size_t)q * nin);
+            m.eval[q] = evals[q]; m.table1[q] = aq.table[0]; m.table2[q] = aq.table[1];
+            if (q == 0) a = aq;
+        }
+        if (rc != SG_OK) return rc;
+        rc = sg_evaluate_multi_fast<T>(m, n_der, a, cp, st);
+        if (rc != SG_ERR_UNSUPPORTED) return rc;
+    }
+    for (int q = 0; q < n_der; ++q) {
+        int rc = sg_evaluate_impl<T>(evals[q], nin, n_samples, n_cp, nout, tables, indices, degree, mdo, ders + (size_t)q * nin, cp,
+                                     weights, stream);
+        if (rc != SG_OK) return rc;
+    }
     return SG_OK;
 }
 
@@ -340,6 +372,14 @@ static int sg_adjoint_push_impl(const sg_adjoint_plan *plan, T *cp, int nin, con
     {                                                                                                                \
         return sg_evaluate_impl<T>(eval, nin, n_samples, n_cp, nout, tables, indices, degree, mdo, der, cp, weights, \
                                    stream);                                                                          \
+    }                                                                                                                \
+    extern "C" int sg_evaluate_multi_##SUF(T *const *evals, int n_der, const int *ders, int nin, const int64_t *n_samples,     \
+                                           const int64_t *n_cp, int nout, const T *const *tables,                   \
+                                           const int32_t *const *indices, const int *degree, const int *mdo,         \
+                                           const T *cp, const T *weights, void *stream)                              \
+    {                                                                                                                \
+        return sg_evaluate_multi_impl<T>(evals, n_der, ders, nin, n_samples, n_cp, nout, tables, indices, degree,    \
+                                         mdo, cp, weights, stream);                                                  \
     }                                                                                                                \
     extern "C" int sg_evaluate_adjoint_##SUF(T *cp, int nin, const int64_t *n_samples, const int64_t *n_cp,          \
                                              int nout, const T *const *tables, const int32_t *const *indices,        \

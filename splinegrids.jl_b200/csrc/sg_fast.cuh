@@ -35,3 +35,9 @@ struct SgM2gDims {
     int rfast;     // layout of the weights: 1 = [block][li][r] (r fastest, 2-D: lanes walk r), 0 = [block][r][li] (3-D: lanes walk li)
 };
 SgM2gDims sg_m2g_dims(int nin, const int64_t *n_samples, const int64_t *n_cp, const int *degree, bool rational, int elem_size);
+
+// evaluate! for several derivative orders in one launch (sg_eval_multi.cuh); SG_ERR_UNSUPPORTED: the caller loops
+template <typename T>
+struct SgMultiArgs;
+template <typename T>
+int sg_evaluate_multi_fast(const SgMultiArgs<T> &m, int n_der, const SgGridArgs<T> &a, const T *cp, cudaStream_t st);

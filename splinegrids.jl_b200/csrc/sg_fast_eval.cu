@@ -8,6 +8,7 @@
 #include "sg_fast.cuh"
 #include "sg_fast_adjoint.cuh"
 #include "sg_fast_eval.cuh"
+#include "sg_eval_multi.cuh"
 
 static int sg_env_int(const char *name, int dflt)
 {
@@ -174,6 +175,51 @@ int sg_evaluate_fast(T *eval, const SgGridArgs<T> &a, const T *cp, const T *weig
         default: return sg_eval2d_by_nout<T, 3, false>(eval, a, cp, weights, st);
     }
 }
+
+// ---- several derivative orders in one launch (2-D, uniform degree 1..3, not rational) ----------------------------
+template <typename T, int P, int ND>
+static int sg_launch_eval2d_multi(const SgMultiArgs<T> &m, const SgGridArgs<T> &a, const T *cp, cudaStream_t st)
+{
+    constexpr int V1 = sizeof(T) == 4 ? 4 : 2;
+    const int threads = 128;
+    const int64_t gx = (a.n_samples[0] + threads * V1 - 1) / (threads * V1);
+    const int chunk = sg_pick_chunk(a.n_samples[1], gx * a.nout, 32, 512, sg_env_int("SG_CHUNK2D", 0));
+    const int64_t gy = (a.n_samples[1] + chunk - 1) / chunk;
+    if (gy > 65535 || a.nout > 65535) return SG_ERR_UNSUPPORTED;
+    bool vec_ok = a.n_samples[0] % V1 == 0;
+    for (int q = 0; q < ND; ++q) vec_ok = vec_ok && reinterpret_cast<uintptr_t>(m.eval[q]) % 16 == 0;
+    const size_t smem = (size_t)chunk * (ND * (P + 1) * sizeof(T) + sizeof(int));
+    dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)a.nout);
+    sg_eval2d_multi_kernel<T, P, V1, ND><<<grid, threads, smem, st>>>(m, a, cp, chunk, vec_ok);
+    g_sg_last_variant = "evaluate_multi2d";
+    SG_AFTER_LAUNCH();
+    return SG_OK;
+}
+
+template <typename T>
+int sg_evaluate_multi_fast(const SgMultiArgs<T> &m, int n_der, const SgGridArgs<T> &a, const T *cp, cudaStream_t st)
+{
+    int p;
+    if (a.nin != 2 || !sg_uniform_degree(a.degree, a.nin, p) || p < 1 || p > 3) return SG_ERR_UNSUPPORTED;
+    if (n_der < 2 || n_der > SG_MULTI_MAX) return SG_ERR_UNSUPPORTED;
+    if (g_sg_policy == 1 || (g_sg_policy != 2 && a.n_total < 32768)) return SG_ERR_UNSUPPORTED;
+    // evaluate! is bound by its output write, which fusing cannot reduce: on C2 (3 x 201 MB out) the fused kernel takes
+    // 0.122 ms against 0.112 ms for three single launches (82 % of HBM each), so large outputs keep the single kernels and
+    // the fused launch serves the sizes where launches and table/control-point re-reads matter (SG_EVAL_MULTI=2 forces it).
+    const double out_bytes = (double)a.n_total * a.nout * n_der * sizeof(T);
+    const int mode = sg_env_int("SG_EVAL_MULTI", 1);
+    if (mode == 0 || (mode == 1 && g_sg_policy != 2 && out_bytes > 64.0e6)) return SG_ERR_UNSUPPORTED;
+#define SG_MULTI_CASE(PP)                                                              \
+    switch (n_der) {                                                                   \
+        case 2: return sg_launch_eval2d_multi<T, PP, 2>(m, a, cp, st);                 \
+        case 3: return sg_launch_eval2d_multi<T, PP, 3>(m, a, cp, st);                 \
+        default: return sg_launch_eval2d_multi<T, PP, 4>(m, a, cp, st);                \
+    }
+    if (p == 1) { SG_MULTI_CASE(1) } else if (p == 2) { SG_MULTI_CASE(2) } else { SG_MULTI_CASE(3) }
+#undef SG_MULTI_CASE
+}
+template int sg_evaluate_multi_fast<float>(const SgMultiArgs<float> &, int, const SgGridArgs<float> &, const float *, cudaStream_t);
+template int sg_evaluate_multi_fast<double>(const SgMultiArgs<double> &, int, const SgGridArgs<double> &, const double *, cudaStream_t);
 
 template int sg_evaluate_fast<float>(float *, const SgGridArgs<float> &, const float *, const float *, cudaStream_t);
 template int sg_evaluate_fast<double>(double *, const SgGridArgs<double> &, const double *, const double *, cudaStream_t);

@@ -189,6 +189,30 @@ def evaluate_(obj, *, derivative_order: Optional[Sequence[int]] = None, control_
     return None
 
 
+def evaluate_multi_(grid: SplineGrid, derivative_orders: Sequence[Sequence[int]], evals: Sequence[torch.Tensor], *,
+                    control_points=None) -> None:
+    """Several ``evaluate!`` calls on the same control points as ONE library call (``sg_evaluate_multi``): what the
+    reference's callers write as back-to-back calls with different ``derivative_order`` and ``eval`` arrays
+    (docs/src/examples_optics.md:189-191, docs/src/examples_pde.md:69-72).  ``evals[q]`` receives
+    ``evaluate!(grid; derivative_order = derivative_orders[q], eval = evals[q])``."""
+    nin = grid.Nin
+    ders = [tuple(int(d) for d in der) for der in derivative_orders]
+    assert len(ders) == len(evals) and len(ders) >= 1
+    control_points = grid.control_points if control_points is None else control_points
+    for der, ev in zip(ders, evals):
+        assert len(der) == nin
+        validate_partial_derivatives(grid.spline_dimensions, der, is_nurbs=grid.is_nurbs())
+        cp = _check_arrays(grid, control_points, ev)
+    fn = getattr(_lib.lib(), "sg_evaluate_multi_" + _lib.suffix(grid.dtype))
+    flat = [d for der in ders for d in der]
+    args = _grid_call_args(grid, (0,) * nin)[:-1]                     # without the single derivative order
+    with torch.cuda.device(grid.device):
+        _lib.check(fn(_lib.ptr_array(list(evals)), C.c_int(len(ders)), _lib.int_array(flat), *args, _lib.ptr(cp),
+                      _lib.ptr(grid.weights), _lib.stream_ptr(grid.device)), "sg_evaluate_multi")
+    after_launch(grid.device)
+    return None
+
+
 def _workspace(grid: SplineGrid) -> torch.Tensor:
     """Adjoint workspace owned by the grid (its raw pointer is baked into prepared calls and captured CUDA graphs, so
     its lifetime is the grid's).  One grid must not run evaluate_adjoint! on two streams at the same time."""

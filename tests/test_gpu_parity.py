@@ -373,6 +373,43 @@ def test_adjoint_plan_invalidated_by_dimension_rebuild(S):
     assert rel_err(S.to_numpy(g), oracle_adjoint(grid, e)) <= 1e-12
 
 
+MULTI_CASES = [
+    # n_cp, degree, n_samples, nout, float type, mdo, derivative tuples
+    ((16, 12), (3, 3), (300, 280), 3, "Float32", 1, [(0, 0), (1, 0), (0, 1)]),            # the optics caller: u, d1 u, d2 u
+    ((16, 12), (3, 3), (300, 280), 2, "Float64", 2, [(0, 0), (2, 0), (0, 2), (1, 1)]),    # four tuples
+    ((9, 14), (2, 2), (513, 77), 1, "Float64", 1, [(1, 0), (0, 1)]),                      # ragged n1, degree 2
+    ((30, 8), (1, 1), (128, 400), 2, "Float32", 1, [(0, 0), (1, 1)]),                     # degree 1
+    ((5, 8, 6), (3, 3, 3), (40, 36, 44), 1, "Float64", 2, [(0, 0, 0), (2, 0, 0), (0, 2, 0), (0, 0, 2)]),   # 3-D (PDE caller): one launch per tuple
+    ((12, 10), (3, 4), (96, 73), 3, "Float64", 1, [(0, 0), (1, 0)]),                      # mixed degrees: one launch per tuple
+]
+
+
+@pytest.mark.parametrize("case", MULTI_CASES, ids=[f"{c[0]}-{c[1]}-{c[4]}-{len(c[6])}ders" for c in MULTI_CASES])
+def test_evaluate_multi_vs_separate_oracle_calls(S, case):
+    """sg_evaluate_multi (row f1): value + partial derivatives in one call == separate oracle evaluations."""
+    from gpu_helpers import make_grid, oracle_evaluate
+    n_cp, deg, n_s, nout, ft, mdo, ders = case
+    grid, cp, w, rng = make_grid(n_cp, deg, n_s, nout, ft, mdo=mdo, seed=61)
+    evs = [torch.full_like(grid.eval, float("nan")) for _ in ders]
+    S.set_kernel_policy(2)
+    try:
+        S.launch_count_reset()
+        S.evaluate_multi_(grid, ders, evs)
+        fused = len(n_cp) == 2 and len(set(deg)) == 1 and deg[0] <= 3
+        assert S.launch_count() == (1 if fused else len(ders))
+        if fused:
+            assert S.last_variant() == "evaluate_multi2d"
+    finally:
+        S.set_kernel_policy(0)
+    tol = _tol(ft)
+    for der, ev in zip(ders, evs):
+        ref = oracle_evaluate(grid, cp, der)
+        assert rel_err(S.to_numpy(ev), ref) <= tol, der
+        assert max_rel_err(S.to_numpy(ev), ref) <= 10 * tol, der
+    with pytest.raises(S.SplineGridsError):
+        S.evaluate_multi_(grid, [tuple(mdo + 1 for _ in n_cp)], evs[:1])
+
+
 def test_evaluate_with_raw_and_reshaped_arrays(S):
     """control_points / eval kwargs accept raw arrays and reshaped flat vectors (test/test_EnzymeExt.jl:24-28,
     ext/SplineGridsLinearMapsExt.jl:26-30)."""

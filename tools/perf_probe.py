@@ -19,6 +19,8 @@ CONFIGS = {
     "C3s": dict(n_cp=(128, 128, 128), deg=(3, 3, 3), n_s=(512, 512, 64), nout=1, ft="Float64"),
     "C4": dict(n_cp=(256, 256), deg=(3, 3), n_s=(8192, 8192), nout=3, ft="Float32", nurbs=True),
     "C5s": dict(n_cp=(250, 250), deg=(2, 2), n_s=(4096, 4096), nout=3, ft="Float32"),
+    "C5d": dict(n_cp=(18, 18), deg=(2, 2), n_s=(500, 500), nout=3, ft="Float32", mdo=1),      # docs-size finest level of C5
+    "M1k": dict(n_cp=(64, 64), deg=(3, 3), n_s=(1024, 1024), nout=3, ft="Float32", mdo=1),
 }
 
 
@@ -94,7 +96,15 @@ def main():
         for pol in [int(p) for p in args.policies.split(",")]:
             S.set_kernel_policy(pol)
             for op in args.ops.split(","):
-                if op == "evaluate":
+                if op == "multi":           # value + first partials (C2's three calls) as one library call
+                    ders = [(0,) * len(cfg["n_cp"])] + [tuple(1 if d == k else 0 for d in range(len(cfg["n_cp"]))) for k in range(len(cfg["n_cp"]))]
+                    evs = [torch.empty_like(grid.eval) for _ in ders]
+                    fn = lambda: S.evaluate_multi_(grid, ders, evs)
+                elif op == "separate":
+                    ders = [(0,) * len(cfg["n_cp"])] + [tuple(1 if d == k else 0 for d in range(len(cfg["n_cp"]))) for k in range(len(cfg["n_cp"]))]
+                    evs = [torch.empty_like(grid.eval) for _ in ders]
+                    fn = lambda: [S.evaluate_(grid, derivative_order=d, eval=e) for d, e in zip(ders, evs)]
+                elif op == "evaluate":
                     fn = lambda: S.evaluate_(grid)
                 else:
                     fn = lambda: S.evaluate_adjoint_(grid, eval=e_in, control_points=g_out, allow_nurbs=True)
