@@ -222,6 +222,73 @@ int sg_gather_zero_active_f32(float *refinement_values, float *cp, int nin, cons
 int sg_gather_zero_active_f64(double *refinement_values, double *cp, int nin, const int64_t *n_cp, int nout,
                               const int32_t *refinement_indices, int64_t n_active, void *stream);
 
+/* ---- construction side of local refinement on the device (scope row f3) --------------------------------------------
+ * K13 build_refinement_matrix_kernel -- src/refinement.jl:3-36 (launcher :53-88): Boehm's single-knot insertion matrix,
+ * (n_basis_old + 1) rows, n_basis_old + degree + 1 non-zeros; knot_span_index as returned by insert_knot (:114-131). */
+int sg_boehm_matrix_f32(int32_t *row_pointer, int32_t *column_start, float *nzval, const float *knots_all_old,
+                        int64_t n_basis_old, int64_t knot_span_index, float knot_new, int degree, void *stream);
+int sg_boehm_matrix_f64(int32_t *row_pointer, int32_t *column_start, double *nzval, const double *knots_all_old,
+                        int64_t n_basis_old, int64_t knot_span_index, double knot_new, int degree, void *stream);
+/* K14 validate_refinement_matrix_kernel -- src/refinement_matrix.jl:134-181: valid_row[i] (uint8) per row. */
+int sg_refmat_validate_i32(uint8_t *valid_row, const int32_t *row_pointer, const int32_t *column_start, int64_t m, int64_t nnz,
+                           int64_t n_columns, void *stream);
+/* K16 refinement_matrix_mul_nonzeros_kernel -- src/refinement_matrix.jl:229-271: per row of C = A * B the number of
+ * non-zeros and the first column.  sg_row_pointer_from_counts: row_pointer = 1 + cumsum (m + 1 entries of scratch, the
+ * last one is the total), total copied to the host (synchronises) -- :300-303.  K15 refinement_matrix_multiplication_kernel
+ * -- :184-227: the values (nzval_C is zero-filled by the callee). */
+int sg_refmat_mul_nonzeros_i32(int32_t *n_nonzero_C, int32_t *column_start_C, const int32_t *row_pointer_A, const int32_t *column_start_A,
+                               int64_t m_A, int64_t nnz_A, const int32_t *row_pointer_B, const int32_t *column_start_B, int64_t m_B,
+                               int64_t nnz_B, int64_t n_columns_B, void *stream);
+int sg_row_pointer_from_counts(int32_t *row_pointer, int64_t *total_host, const int32_t *counts, int64_t m, void *stream);
+int sg_refmat_mul_values_f32(float *nzval_C, int64_t nnz_C, const int32_t *row_pointer_C, const int32_t *column_start_C,
+                             const int32_t *row_pointer_A, const int32_t *column_start_A, const float *nzval_A, int64_t m_A, int64_t nnz_A,
+                             const int32_t *row_pointer_B, const int32_t *column_start_B, const float *nzval_B, int64_t m_B, int64_t nnz_B,
+                             void *stream);
+int sg_refmat_mul_values_f64(double *nzval_C, int64_t nnz_C, const int32_t *row_pointer_C, const int32_t *column_start_C,
+                             const int32_t *row_pointer_A, const int32_t *column_start_A, const double *nzval_A, int64_t m_A, int64_t nnz_A,
+                             const int32_t *row_pointer_B, const int32_t *column_start_B, const double *nzval_B, int64_t m_B, int64_t nnz_B,
+                             void *stream);
+/* K17 collect_refinement_matrix_kernel -- src/refinement_matrix.jl:329-363: dense (m, n) column-major, zero-filled by the callee. */
+int sg_refmat_collect_f32(float *out, const int32_t *row_pointer, const int32_t *column_start, const float *nzval, int64_t m, int64_t n,
+                          int64_t nnz, void *stream);
+int sg_refmat_collect_f64(double *out, const int32_t *row_pointer, const int32_t *column_start, const double *nzval, int64_t m, int64_t n,
+                          int64_t nnz, void *stream);
+/* K18 refinement_values_new_kernel -- src/control_points.jl:427-456: rows < n_old copy the old values, the others read the
+ * refined control points at their (1-based) indices. */
+int sg_refinement_values_new_f32(float *values_new, const float *values_old, int64_t n_old, const float *control_points_refined, int nin,
+                                 const int64_t *n_cp, int nout, const int32_t *refinement_indices_new, int64_t n_new, void *stream);
+int sg_refinement_values_new_f64(double *values_new, const double *values_old, int64_t n_old, const double *control_points_refined, int nin,
+                                 const int64_t *n_cp, int nout, const int32_t *refinement_indices_new, int64_t n_new, void *stream);
+/* Flag (Bool) variants for deactivate_overwritten_control_points! -- src/control_points.jl:584-680, src/utils.jl:237-247:
+ * K7 on a Flag array (set the active entries to `value`), K6 (src/adjoint.jl:117-121: B .= false, B[J] = true for every J in
+ * the structural window of a true Y[I]), K8 (read the flag at the active entries).  Flags are uint8 0/1. */
+int sg_scatter_active_flag(uint8_t *cp_flags, int nin, const int64_t *n_cp, const int32_t *refinement_indices, int64_t n_active,
+                           int value, void *stream);
+int sg_refmat_mul_adjoint_flag(uint8_t *B, const uint8_t *Y, int ndims, const int64_t *sizeY, const int64_t *sizeB, int n_ref,
+                               const int *dims, const int32_t *const *row_ptr, const int32_t *const *col_start, const int64_t *nnz,
+                               void *stream);
+int sg_gather_active_flag(uint8_t *values, const uint8_t *cp_flags, int nin, const int64_t *n_cp, const int32_t *refinement_indices,
+                          int64_t n_active, void *stream);
+/* findall(flags) (invert = 0) / findall(.!flags) (invert = 1): ascending 0-based positions; count on the host (synchronises).
+ * scratch: n + 1 Int32. */
+int sg_compact_flags(int32_t *out_idx, int64_t *count_host, const uint8_t *flags, int64_t n, int invert, int32_t *scratch, void *stream);
+/* out[r, c] = in[row_idx[r], c] for column-major (n_in, ncols) matrices (row selection `A[where, :]`, :669-670). */
+int sg_gather_rows_f32(float *out, const float *in, const int32_t *row_idx, int64_t n_in, int64_t n_out, int ncols, void *stream);
+int sg_gather_rows_f64(double *out, const double *in, const int32_t *row_idx, int64_t n_in, int64_t n_out, int ncols, void *stream);
+int sg_gather_rows_i32(int32_t *out, const int32_t *in, const int32_t *row_idx, int64_t n_in, int64_t n_out, int ncols, void *stream);
+/* error_informed_local_refinement! -- src/control_points.jl:556-566: grid_err = sum over outputs, threshold =
+ * threshold_factor * mean(grid_err) (fixed summation order), flags = grid_err > threshold.  scratch: ceil(cp_total / 256) T. */
+int sg_error_flags_f32(uint8_t *flags, float *grid_err, float *threshold_out_or_null, const float *cp_err, int64_t cp_total, int nout,
+                       float threshold_factor, float *scratch_block_sums, void *stream);
+int sg_error_flags_f64(uint8_t *flags, double *grid_err, double *threshold_out_or_null, const double *cp_err, int64_t cp_total, int nout,
+                       double threshold_factor, double *scratch_block_sums, void *stream);
+/* (n, nin) 1-based Int32 index matrix of 0-based linear positions in a column-major (n_cp...) grid (findall + collect_indices). */
+int sg_indices_from_linear_i32(int32_t *indices, const int32_t *linear0, int64_t n, int nin, const int64_t *n_cp, void *stream);
+/* unique(vcat(old, new); dims = 1) keeping first occurrences (src/control_points.jl:482-494, on the CPU in the reference):
+ * keep_new[i] = 1 iff row i of new_indices is the first row naming its control point.  first_row_scratch: prod(n_cp) Int32. */
+int sg_unique_new_rows_i32(uint8_t *keep_new, const int32_t *old_indices, int64_t n_old, const int32_t *new_indices, int64_t n_new,
+                           int nin, const int64_t *n_cp, int32_t *first_row_scratch, void *stream);
+
 /* ---- multi-GPU: gradient all-reduce (new; the reference is single-device) -------------------
  * One communicator per process/GPU.  `unique_id` is a 128-byte ncclUniqueId produced by
  * sg_comm_unique_id on rank 0 and distributed by the host (MPI, torch.distributed store, files).

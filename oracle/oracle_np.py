@@ -742,9 +742,15 @@ def activate_local_refinement(lrcp: LocallyRefinedCP, refinement_indices: np.nda
 
 def activate_local_control_point_range(lrcp: LocallyRefinedCP, *ranges: Tuple[int, int]) -> None:
     """``activate_local_control_point_range!`` -- src/control_points.jl:531-539.
-    Each range is a 1-based inclusive ``(lo, hi)``; index order = Iterators.product (dim 1 fastest)."""
+    Each range is a 1-based inclusive ``(lo, hi)``.  Row order: the reference builds the Nin-dimensional array of
+    index vectors with ``Iterators.product`` (dim 1 fastest) and flattens its ADJOINT, ``reduce(vcat, A')`` (:537),
+    i.e. for Nin = 2 the rows come out with dimension 2 fastest; for Nin = 1 the order is unchanged; for Nin >= 3 the
+    adjoint of an N-d array does not exist and the reference call errors (kept here as dim 1 fastest)."""
     rs = [range(lo, hi + 1) for lo, hi in ranges]
-    rows = [tuple(reversed(t)) for t in itertools.product(*reversed(rs))]
+    if len(rs) == 2:
+        rows = [(i, j) for i in rs[0] for j in rs[1]]
+    else:
+        rows = [tuple(reversed(t)) for t in itertools.product(*reversed(rs))]
     activate_local_refinement(lrcp, np.array(rows, dtype=np.int32).reshape(len(rows), len(rs)))
 
 

@@ -240,30 +240,36 @@ def activate_local_refinement_(control_points: LocallyRefinedControlPoints, refi
                                refinement_index: Optional[int] = None) -> None:
     """``activate_local_refinement!`` -- src/control_points.jl:470-516.  New active control points take the
     current refined value (geometry unchanged); duplicates are dropped keeping first occurrences
-    (``unique(...; dims=1)``, done on the CPU in the reference too, :482-494)."""
+    (``unique(vcat(old, new); dims = 1)``: on the CPU in the reference, :482-494; here a first-row table on the device,
+    ``sg_unique_new_rows``), then K18 fills the values.  Nothing but the number of kept rows comes back to the host."""
+    from . import device_setup as D
     level = len(control_points.local_refinements) if refinement_index is None else refinement_index
     lr = control_points.local_refinements[level - 1]
     cp = control_points.control_points_refined[level - 1]
     nin = cp.dim() - 1
-    new = refinement_indices.detach().cpu().numpy() if isinstance(refinement_indices, torch.Tensor) \
-        else np.asarray(refinement_indices)
-    assert new.ndim == 2 and new.shape[1] == nin, \
+    if isinstance(refinement_indices, torch.Tensor):
+        new = refinement_indices.to(device=cp.device, dtype=torch.int32)
+    else:
+        new = to_device(np.asarray(refinement_indices, dtype=np.int32).reshape(-1, nin), device=cp.device)
+    assert new.dim() == 2 and new.shape[1] == nin, \
         "Number of indices per control point must match the number of input dimensions."
-    old = to_numpy(lr.refinement_indices).reshape(-1, nin)
-    allidx = np.concatenate([old, new.astype(np.int32)], axis=0)
-    _, first = np.unique(allidx, axis=0, return_index=True)
-    keep = np.sort(first)
-    idx_new = allidx[keep]
-    n_old = old.shape[0]
-    assert np.array_equal(keep[:n_old], np.arange(n_old))      # existing rows are unique already
-    idx_dev = to_device(idx_new, device=cp.device)
-    vals = jl_empty((idx_new.shape[0], cp.shape[-1]), cp.dtype, cp.device)
-    vals[:n_old] = lr.refinement_values
-    if idx_new.shape[0] > n_old:                              # K18 refinement_values_new_kernel (:427-456)
-        sel = tuple(torch.from_numpy(idx_new[n_old:, d].astype(np.int64) - 1).to(cp.device) for d in range(nin))
-        vals[n_old:] = cp[sel]
+    new = as_colmajor(new)
+    old = as_colmajor(lr.refinement_indices.reshape(-1, nin)) if lr.refinement_indices.numel() else \
+        jl_empty((0, nin), torch.int32, cp.device)
+    n_old = int(old.shape[0])
+    if new.shape[0] > 0:
+        keep = D.unique_new_rows(old, new, cp.shape[:-1])
+        rows = D.compact_flags(keep)
+        kept = D.gather_rows(new, rows)
+    else:
+        kept = new
+    idx_new = jl_empty((n_old + kept.shape[0], nin), torch.int32, cp.device)
+    idx_new[:n_old] = old
+    idx_new[n_old:] = kept
+    vals_old = lr.refinement_values if n_old else jl_empty((0, cp.shape[-1]), cp.dtype, cp.device)
+    vals = D.refinement_values_new(as_colmajor(vals_old), cp, idx_new)       # K18 refinement_values_new_kernel (:427-456)
     control_points.local_refinements[level - 1] = LocalRefinement(lr.dims_refinement, lr.refinement_matrices,
-                                                                  idx_dev, vals)
+                                                                  idx_new, vals)
 
 
 def activate_local_control_point_range_(spline_grid_or_cp, *ranges) -> None:
@@ -272,15 +278,23 @@ def activate_local_control_point_range_(spline_grid_or_cp, *ranges) -> None:
     cp = getattr(spline_grid_or_cp, "control_points", spline_grid_or_cp)
     rs = [r if isinstance(r, range) else range(r[0], r[1] + 1) for r in ranges]
     assert len(rs) == cp.Nin
-    rows = [tuple(reversed(t)) for t in itertools.product(*reversed(rs))]   # Iterators.product: dim 1 fastest
+    # Row order of the reference: ``reduce(vcat, A')`` of the Iterators.product array (:535-537) -- for Nin = 2 the
+    # adjoint makes dimension 2 the fastest; Nin = 1 is unchanged; Nin >= 3 errors in the reference (an N-d array has no
+    # adjoint), here it keeps the product order (dimension 1 fastest).
+    if len(rs) == 2:
+        rows = list(itertools.product(*rs))
+    else:
+        rows = [tuple(reversed(t)) for t in itertools.product(*reversed(rs))]
     activate_local_refinement_(cp, np.array(rows, dtype=np.int32).reshape(len(rows), len(rs)))
 
 
 def deactivate_overwritten_control_points_(control_points: LocallyRefinedControlPoints,
                                            local_refinement_level: Optional[int] = None) -> None:
-    """``deactivate_overwritten_control_points!`` -- src/control_points.jl:584-680.  The reference pushes a
-    Boolean ``Flag`` through ``L* . O2`` (adjoint of the refinement with the structural support of the
-    matrices); here the same OR-propagation is done on the host with boolean support matrices."""
+    """``deactivate_overwritten_control_points!`` -- src/control_points.jl:584-680, on the device like the reference:
+    a Boolean ``Flag`` array of the next level starts all true, the next level's active entries are set false (K7 on
+    Flags), ``mult_adjoint!`` on Flags ORs each structural window back to this level (K6, src/adjoint.jl:117-121), K8
+    reads the flag of every active control point of this level, ``findall`` + row selection keep the visible ones."""
+    from . import device_setup as D
     if local_refinement_level is None:
         for level in range(len(control_points.local_refinements) - 1, 0, -1):
             deactivate_overwritten_control_points_(control_points, level)
@@ -289,20 +303,18 @@ def deactivate_overwritten_control_points_(control_points: LocallyRefinedControl
     assert 1 <= local_refinement_level <= len(lrs) - 1
     lr, lr_next = lrs[local_refinement_level - 1], lrs[local_refinement_level]
     nin = control_points.Nin
+    dev = control_points.device
+    shape = tuple(control_points.control_points_refined[local_refinement_level - 1].shape[:-1])
     shape_next = tuple(control_points.control_points_refined[local_refinement_level].shape[:-1])
-    visible = np.ones(shape_next, dtype=bool)
-    idx_next = to_numpy(lr_next.refinement_indices).reshape(-1, nin).astype(np.int64) - 1
-    if idx_next.shape[0]:
-        visible[tuple(idx_next[:, d] for d in range(nin))] = False
-    for A, d in zip(lr_next.refinement_matrices, lr_next.dims_refinement):
-        cs, ce = A.column_ranges()
-        support = np.zeros((A.n, A.m), dtype=np.int64)            # transpose support
-        for i in range(A.m):
-            support[cs[i] - 1:ce[i], i] = 1
-        visible = np.moveaxis(np.tensordot(support, visible.astype(np.int64), axes=(1, d - 1)), 0, d - 1) > 0
-    idx = to_numpy(lr.refinement_indices).reshape(-1, nin).astype(np.int64) - 1
-    keep = np.flatnonzero(visible[tuple(idx[:, d] for d in range(nin))]) if idx.shape[0] else np.zeros(0, np.int64)
-    keep_dev = torch.from_numpy(keep).to(control_points.device)
-    lrs[local_refinement_level - 1] = LocalRefinement(
-        lr.dims_refinement, lr.refinement_matrices,
-        as_colmajor(lr.refinement_indices[keep_dev]), as_colmajor(lr.refinement_values[keep_dev]))
+    flags_next = torch.ones(int(np.prod(shape_next)), dtype=torch.uint8, device=dev)      # ones(Flag, ...) :636
+    if lr_next.n_active:
+        D.scatter_active_flag(flags_next, shape_next, as_colmajor(lr_next.refinement_indices.reshape(-1, nin)), False)
+    flags = D.mult_adjoint_flag(shape, lr_next.refinement_matrices, flags_next, shape_next, lr_next.dims_refinement)
+    if lr.n_active:
+        idx = as_colmajor(lr.refinement_indices.reshape(-1, nin))
+        visible = D.gather_active_flag(flags, shape, idx)
+        rows = D.compact_flags(visible)                                # findall(f -> f.flag, refinement_values_) :667
+        idx_new, vals_new = D.gather_rows(idx, rows), D.gather_rows(as_colmajor(lr.refinement_values), rows)
+    else:
+        idx_new, vals_new = lr.refinement_indices, lr.refinement_values
+    lrs[local_refinement_level - 1] = LocalRefinement(lr.dims_refinement, lr.refinement_matrices, idx_new, vals_new)

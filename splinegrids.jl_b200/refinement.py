@@ -21,23 +21,16 @@ from .spline_dimension import SplineDimension, build_, evaluate_dimension_, set_
 from .spline_grid import SplineGrid, evaluate_adjoint_
 
 
-def boehm_refinement_matrix(knots_all_old: np.ndarray, degree: int, knot_span_index: int, knot_new,
+def boehm_refinement_matrix(knots_all_old, degree: int, knot_span_index: int, knot_new,
                             device=None) -> RefinementMatrix:
-    """``RefinementMatrix(spline_dimension, knot_span_index, knot_new)`` (K13) -- src/refinement.jl:3-88:
-    Boehm's single-knot insertion as an (n+1) x n banded matrix."""
-    T = knots_all_old.dtype.type
-    n = len(knots_all_old) - degree - 1
-    k, p = int(knot_span_index), int(degree)
-    i = np.arange(1, n + 2)
-    left, mid = i <= k - p, (i > k - p) & (i <= k)
-    rp = np.where(left, i, np.where(mid, 2 * i - k + p - 1, i + p)).astype(np.int32)
-    cs = np.where(left, i, i - 1).astype(np.int32)
-    nz = np.ones(n + p + 1, dtype=knots_all_old.dtype)
-    im = i[mid]
-    alpha = (T(knot_new) - knots_all_old[im - 1]) / (knots_all_old[im + p - 1] - knots_all_old[im - 1])
-    nz[rp[mid] - 1] = T(1) - alpha
-    nz[rp[mid]] = alpha
-    return RefinementMatrix(n + 1, n, rp, cs, nz, device=device)
+    """``RefinementMatrix(spline_dimension, knot_span_index, knot_new)`` (K13, on the device) -- src/refinement.jl:3-88:
+    Boehm's single-knot insertion as an (n+1) x n banded matrix.  ``knots_all_old``: device tensor or host array."""
+    from . import device_setup as D
+    if not isinstance(knots_all_old, torch.Tensor):
+        knots_all_old = to_device(np.asarray(knots_all_old), device=device)
+    n = knots_all_old.numel() - int(degree) - 1
+    rp, cs, nz = D.boehm_matrix(knots_all_old, int(degree), int(knot_span_index), knot_new)
+    return RefinementMatrix(n + 1, n, rp, cs, nz, device=knots_all_old.device)
 
 
 def insert_knot(obj, *args, **kwargs):
@@ -64,7 +57,7 @@ def _insert_knot_sd(sd: SplineDimension, knot_new, recompute_sample_indices: boo
                     evaluate: bool = True) -> Tuple[SplineDimension, RefinementMatrix]:
     """src/refinement.jl:161-186."""
     kv_new, k = _insert_knot_kv(sd.knot_vector, knot_new)
-    R = boehm_refinement_matrix(to_numpy(sd.knot_vector.knots_all), sd.degree, k, knot_new, device=sd.device)
+    R = boehm_refinement_matrix(sd.knot_vector.knots_all, sd.degree, k, knot_new, device=sd.device)
     sd_new = sd.with_knot_vector(kv_new)
     if recompute_sample_indices:
         set_sample_indices_(sd_new)
@@ -155,10 +148,12 @@ def error_informed_local_refinement_(grid: SplineGrid, error: torch.Tensor, thre
     finest control grid with the adjoint (K4), sum over outputs, activate every control point above
     ``threshold_factor * mean``."""
     assert tuple(error.shape) == tuple(grid.eval.shape), "The error array must have the same size as the eval array."
+    from . import device_setup as D
     cp_err = torch.zeros_like(obtain(grid.control_points))
     evaluate_adjoint_(grid, eval=error, control_points=cp_err)
-    grid_err = to_numpy(cp_err.sum(dim=grid.Nin))
-    threshold = threshold_factor * grid_err.sum() / grid_err.size
-    hit = np.argwhere(grid_err > threshold)
-    order = np.lexsort(tuple(hit[:, d] for d in range(grid.Nin)))          # findall: column-major order
-    activate_local_refinement_(grid.control_points, (hit[order] + 1).astype(np.int32))
+    # sum over outputs, threshold = factor * mean, findall(> threshold) in column-major order, CartesianIndex -> (n, Nin)
+    # Int32 matrix: all on the device (sg_error_flags, sg_compact_flags, sg_indices_from_linear)
+    flags = D.error_flags(cp_err, float(threshold_factor))
+    hit = D.compact_flags(flags)
+    idx = D.indices_from_linear(hit, cp_err.shape[:-1])
+    activate_local_refinement_(grid.control_points, idx)

@@ -1,9 +1,9 @@
 """``RefinementMatrix`` and its application ``mult!`` / ``mult_adjoint!`` -- mirrors
 src/refinement_matrix.jl and src/adjoint.jl:85-152 of the reference.
 
-The APPLICATION (K5/K6) runs on the device through the C ABI.  Construction, validation, the
-sparse product and ``collect`` are set-up-time operations (SURVEY.md section 8f "next"); they run on the host
-in numpy on the small index/value arrays, which are then mirrored to the device.
+The application (K5/K6) AND the set-up algebra -- validation (K14), the sparse product (K16 + scan + K15) and
+``collect`` (K17) -- run on the device through the C ABI (``device_setup.py``); the arrays live in device memory and
+the ``*_host`` numpy mirrors are fetched lazily, only when host code (printing, indexing, tests) asks for them.
 """
 from __future__ import annotations
 
@@ -29,23 +29,49 @@ class RefinementMatrix:
     numpy mirrors used by the set-up algebra."""
 
     def __init__(self, m: int, n: int, row_pointer, column_start, nzval, device=None, validate: bool = True):
-        rp = _host(row_pointer).astype(np.int32)
-        cs = _host(column_start).astype(np.int32)
-        nz = _host(nzval)
-        if nz.dtype not in (np.float32, np.float64):
-            nz = nz.astype(np.float64)
-        assert len(rp) == len(cs) == m
-        assert np.array_equal(rp, np.sort(rp))
         self.m, self.n = int(m), int(n)
-        self.row_pointer_host, self.column_start_host, self.nzval_host = rp, cs, nz
+        self._rp_h = self._cs_h = self._nz_h = None
+        on_dev = all(isinstance(t, torch.Tensor) and t.is_cuda for t in (row_pointer, column_start, nzval))
+        if on_dev:                                    # built on the device (K13 / K15): no host round trip
+            self.row_pointer = row_pointer.to(torch.int32).contiguous()
+            self.column_start = column_start.to(torch.int32).contiguous()
+            self.nzval = nzval.contiguous()
+        else:
+            rp = _host(row_pointer).astype(np.int32)
+            cs = _host(column_start).astype(np.int32)
+            nz = _host(nzval)
+            if nz.dtype not in (np.float32, np.float64):
+                nz = nz.astype(np.float64)
+            assert np.array_equal(rp, np.sort(rp))
+            self._rp_h, self._cs_h, self._nz_h = rp, cs, nz
+            dev = require_cuda(device)
+            self.row_pointer = torch.from_numpy(rp).to(dev)
+            self.column_start = torch.from_numpy(cs).to(dev)
+            self.nzval = torch.from_numpy(nz).to(dev)
+        assert self.row_pointer.numel() == self.column_start.numel() == self.m
         if validate:
             bad = self.invalid_rows()
             if bad:
                 raise SplineGridsError(f"Invalid rows: [{', '.join(str(b) for b in bad)}].")
-        dev = require_cuda(device)
-        self.row_pointer = torch.from_numpy(rp).to(dev)
-        self.column_start = torch.from_numpy(cs).to(dev)
-        self.nzval = torch.from_numpy(nz).to(dev)
+
+    # -- lazily fetched host mirrors --------------------------------------------------------------
+    @property
+    def row_pointer_host(self) -> np.ndarray:
+        if self._rp_h is None:
+            self._rp_h = self.row_pointer.cpu().numpy()
+        return self._rp_h
+
+    @property
+    def column_start_host(self) -> np.ndarray:
+        if self._cs_h is None:
+            self._cs_h = self.column_start.cpu().numpy()
+        return self._cs_h
+
+    @property
+    def nzval_host(self) -> np.ndarray:
+        if self._nz_h is None:
+            self._nz_h = self.nzval.cpu().numpy()
+        return self._nz_h
 
     # -- structure helpers (src/refinement_matrix.jl:103-125) -----------------------------------
     def _row_lengths(self) -> np.ndarray:
@@ -53,20 +79,17 @@ class RefinementMatrix:
         return nxt - self.row_pointer_host.astype(np.int64)
 
     def column_ranges(self) -> Tuple[np.ndarray, np.ndarray]:
-        """(column_start, column_end) per row, 1-based inclusive."""
+        """(column_start, column_end) per row, 1-based inclusive (host arrays)."""
         cs = self.column_start_host.astype(np.int64)
         return cs, cs + self._row_lengths() - 1
 
     def invalid_rows(self):
-        """``validate_refinement_matrix_kernel`` -- src/refinement_matrix.jl:134-181 (1-based rows)."""
-        cs, ce = self.column_ranges()
-        ok = ce >= cs
-        ok &= ~ok | ((cs >= 1) & (ce <= self.n))
-        ok[0] = (cs[0] == 1) and (self.row_pointer_host[0] == 1)
-        prev_ok = ok.copy()
-        prev_ok[1:] &= (cs[:-1] <= cs[1:]) & (cs[1:] <= ce[:-1] + 1)
-        prev_ok[1:] &= ~prev_ok[1:] | (ce[1:] >= ce[:-1])
-        return [int(i) + 1 for i in np.flatnonzero(~prev_ok)]
+        """``validate_refinement_matrix_kernel`` (K14, on the device) -- src/refinement_matrix.jl:134-181: 1-based numbers
+        of the invalid rows (``findall(.!valid_row)``)."""
+        from . import device_setup as D
+        valid = D.refmat_valid_rows(self.row_pointer, self.column_start, self.nzval.numel(), self.n)
+        bad = D.compact_flags(valid, invert=True)
+        return [int(i) + 1 for i in bad.cpu().tolist()] if bad.numel() else []
 
     @property
     def shape(self):
@@ -99,41 +122,27 @@ class RefinementMatrix:
         return self.nzval_host.dtype.type(0)
 
     def collect(self) -> np.ndarray:
-        """``collect(A)`` -- dense host matrix, src/refinement_matrix.jl:329-363."""
-        out = np.zeros((self.m, self.n), dtype=self.nzval_host.dtype)
-        cs, ce = self.column_ranges()
-        for i in range(self.m):
-            p = self.row_pointer_host[i] - 1
-            out[i, cs[i] - 1:ce[i]] = self.nzval_host[p:p + ce[i] - cs[i] + 1]
-        return out
+        """``collect(A)`` (K17, on the device) -- dense matrix, src/refinement_matrix.jl:329-363 (returned as numpy)."""
+        from . import device_setup as D
+        return D.refmat_collect(self).cpu().numpy()
+
+    def collect_device(self) -> torch.Tensor:
+        """``collect(A)`` as a column-major device array."""
+        from . import device_setup as D
+        return D.refmat_collect(self)
 
     def __matmul__(self, other: "RefinementMatrix") -> "RefinementMatrix":
-        """``A * B`` -- src/refinement_matrix.jl:273-327.  Row i of C spans the union of the windows of the
-        rows of B selected by row i of A (contiguous because B's row windows are monotone and touching);
-        terms are accumulated in ascending k like the reference kernel (:203-227)."""
+        """``A * B`` -- src/refinement_matrix.jl:273-327 on the device: K16 (non-zeros and first column per row), exclusive
+        scan for the row pointers, K15 (values, terms accumulated in ascending k like the reference kernel)."""
+        from . import device_setup as D
         A, B = self, other
         if A.n != B.m:
             raise ValueError("DimensionMismatch: Inner dimensions must match")
-        a0, a1 = A.column_ranges()
-        b0, b1 = B.column_ranges()
-        c0 = b0[a0 - 1]
-        c1 = b1[a1 - 1]
-        lens = c1 - c0 + 1
-        rp = np.concatenate(([1], 1 + np.cumsum(lens[:-1]))).astype(np.int32)
-        nz = np.zeros(int(lens.sum()), dtype=A.nzval_host.dtype)
-        for i in range(A.m):
-            row = nz[rp[i] - 1: rp[i] - 1 + lens[i]]
-            pa = A.row_pointer_host[i] - 1
-            for k in range(a0[i], a1[i] + 1):
-                pb = B.row_pointer_host[k - 1] - 1
-                lb = b1[k - 1] - b0[k - 1] + 1
-                s = b0[k - 1] - c0[i]
-                row[s:s + lb] += A.nzval_host[pa] * B.nzval_host[pb:pb + lb]
-                pa += 1
-        return RefinementMatrix(A.m, B.n, rp, c0.astype(np.int32), nz, device=A.device)
+        rp, cs, nz = D.refmat_matmul(A, B)
+        return RefinementMatrix(A.m, B.n, rp, cs, nz, device=A.device)
 
     def __repr__(self):
-        return f"RefinementMatrix({self.m}x{self.n}, nnz={len(self.nzval_host)}, {self.dtype})"
+        return f"RefinementMatrix({self.m}x{self.n}, nnz={self.nzval.numel()}, {self.dtype})"
 
 
 def _host(a) -> np.ndarray:

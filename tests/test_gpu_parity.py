@@ -918,6 +918,72 @@ def test_g9_locally_refined_least_squares_fitting(S):
 # ---------------------------------------------------------------------------------------------
 
 
+@pytest.mark.parametrize("ft", ["Float32", "Float64"])
+def test_device_refinement_setup_kernels_vs_oracle(S, ft):
+    """Scope row f3: K13 (Boehm matrix), K16 + scan + K15 (sparse product), K14 (validation), K17 (collect) on the device
+    are BIT-identical to the oracle's restatement of the reference kernels; K18 + unique + Flag pipeline + error-informed
+    flags against numpy restatements."""
+    from gpu_helpers import O
+    from splinegrids_jl_b200 import device_setup as D
+    npdt = np.float32 if ft == "Float32" else np.float64
+    tdt = torch.float32 if ft == "Float32" else torch.float64
+    rng = np.random.default_rng(71)
+    # K13 + product chain: insert four knots one after the other into a random clamped knot vector of degree 3
+    p, nb = 3, 9
+    kv, mu, ka = O.clamped_knot_vector(nb, p, npdt, distribution="random", rng=rng)
+    R_dev, R_ref = None, None
+    for knot_new in (0.31, 0.62, 0.05, 0.93):
+        kvn, mun, k = O.insert_knot(kv, mu, npdt(knot_new))
+        ref = O.boehm_matrix(ka, p, k, npdt(knot_new))
+        dev = S.boehm_refinement_matrix(S.to_device(ka), p, k, npdt(knot_new))
+        assert np.array_equal(dev.row_pointer_host, ref.row_pointer) and np.array_equal(dev.column_start_host, ref.column_start)
+        assert np.array_equal(dev.nzval_host, ref.nzval)                    # bit-identical (no contraction)
+        R_dev = dev if R_dev is None else dev @ R_dev
+        R_ref = ref if R_ref is None else O.refmat_matmul(ref, R_ref)
+        assert np.array_equal(R_dev.row_pointer_host, R_ref.row_pointer) and np.array_equal(R_dev.column_start_host, R_ref.column_start)
+        assert np.array_equal(R_dev.nzval_host, R_ref.nzval)
+        assert np.array_equal(R_dev.collect(), R_ref.dense())               # K17
+        kv, mu, ka = kvn, mun, O.expand_knot_vector(kvn, mun)
+    # K14: rows 2 and 3 invalid (gap after row 1, then a row ending before the previous one)
+    bad = np.zeros((4, 5), dtype=npdt)
+    bad[0, 0] = 1; bad[1, 3:5] = 1; bad[2, 3] = 1; bad[3, 3:5] = 1
+    with pytest.raises(S.SplineGridsError, match=r"Invalid rows: \[2, 3\]"):
+        S.refinement_matrix_from_dense(bad)
+    # unique(vcat(old, new); dims = 1) + K18
+    n_cp, nout = (7, 6), 2
+    cp = S.to_device(np.asfortranarray(rng.random(n_cp + (nout,)).astype(npdt)))
+    old = np.array([[1, 1], [3, 2], [7, 6]], dtype=np.int32)
+    new = np.array([[3, 2], [2, 2], [2, 2], [5, 6], [1, 1], [4, 4]], dtype=np.int32)
+    keep = D.unique_new_rows(S.to_device(old), S.to_device(new), n_cp)
+    assert keep.cpu().tolist() == [0, 1, 0, 1, 0, 1]
+    rows = D.compact_flags(keep)
+    assert rows.cpu().tolist() == [1, 3, 5]
+    kept = D.gather_rows(S.to_device(new), rows)
+    assert np.array_equal(S.to_numpy(kept), new[[1, 3, 5]])
+    idx_all = S.to_device(np.concatenate([old, new[[1, 3, 5]]]))
+    vals_old = S.to_device(np.asfortranarray(rng.random((3, nout)).astype(npdt)))
+    vals = S.to_numpy(D.refinement_values_new(vals_old, cp, idx_all))
+    cpn = S.to_numpy(cp)
+    assert np.array_equal(vals[:3], S.to_numpy(vals_old))
+    assert np.array_equal(vals[3:], np.stack([cpn[1, 1], cpn[4, 5], cpn[3, 3]]))
+    # error-informed flags: grid error = sum over outputs, threshold = factor * mean
+    err = np.asfortranarray(rng.random((40, 30, 3)).astype(npdt))
+    flags = D.error_flags(S.to_device(err), 1.25).cpu().numpy().reshape((40, 30), order="F").astype(bool)
+    ge = err.sum(axis=2)
+    thr = npdt(1.25) * ge.sum() / ge.size
+    expect = ge > thr
+    assert np.count_nonzero(flags != expect) <= 2                           # ties within rounding of the mean only
+    hit = D.compact_flags(S.to_device(np.ascontiguousarray(expect.ravel(order="F").astype(np.uint8))))
+    idx = S.to_numpy(D.indices_from_linear(hit, (40, 30)))
+    ref_idx = np.argwhere(expect.T)[:, ::-1] + 1                            # column-major findall order, 1-based
+    assert np.array_equal(idx, ref_idx.astype(np.int32))
+    # scan / compaction across several scan blocks
+    big = (rng.random(5000) > 0.7).astype(np.uint8)
+    pos = D.compact_flags(S.to_device(big))
+    assert np.array_equal(pos.cpu().numpy(), np.flatnonzero(big).astype(np.int32))
+    assert np.array_equal(D.compact_flags(S.to_device(big), invert=True).cpu().numpy(), np.flatnonzero(big == 0).astype(np.int32))
+
+
 def test_insert_and_collect_indices_kernels(S):
     """K11 `insert_kernel` (src/util_kernels.jl:69-79) and K12 `collect_indices_kernel` (:81-88)."""
     import ctypes as C
