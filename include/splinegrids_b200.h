@@ -20,7 +20,13 @@
  *    asynchronous on that stream; the reference synchronises after every launch
  *    (`synchronize(backend)`), which the host shim reproduces with one stream synchronize.
  *  - Return value: 0 = OK; >0 = cudaError_t; <0 = sg_status below.  Nothing throws, nothing
- *    allocates caller-visible memory, there is no global mutable state besides the launch counter.
+ *    allocates caller-visible memory.  The COMPUTE entry points keep no state between calls and may be
+ *    called concurrently from several host threads on different streams (per-call stream, per-call
+ *    workspace, per-handle plan).  Process-wide state exists only in the TEST / BENCHMARK hooks of the
+ *    "library info" section below -- the launch counter (atomic), sg_set_kernel_policy, sg_last_variant and
+ *    sg_profile_adjoint_main -- which are not meant for concurrent use, and in the lazily resolved NCCL
+ *    function table (initialised once, thread-safe).
+ *  - Every exported call opens an NVTX range named after the entry point (visible in Nsight Systems).
  *  - There is NO CPU fallback: without a CUDA device every compute entry point returns an error.
  */
 #ifndef SPLINEGRIDS_B200_H

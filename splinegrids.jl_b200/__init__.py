@@ -24,6 +24,7 @@ from .refinement_matrix import (RefinementMatrix, mult_, mult_adjoint_, refineme
 from .spline_dimension import SplineDimension, build_, decompress, set_sample_indices_
 from .spline_grid import NURBSGrid, SplineGrid, evaluate_, evaluate_adjoint_, evaluate_multi_
 from .validation import SplineGridsError
+from .autograd import evaluate_autograd, make_zero_
 
 __all__ = [
     "SplineDimension", "SplineGrid", "NURBSGrid", "KnotVector", "RefinementMatrix", "DefaultControlPoints",
@@ -35,5 +36,5 @@ __all__ = [
     "jl_zeros", "jl_ones", "jl_empty", "reshape_colmajor", "is_colmajor", "as_colmajor", "set_synchronous",
     "is_synchronous", "asynchronous", "set_kernel_policy", "last_variant", "launch_count", "launch_count_reset",
     "SplineGridsError", "SplineGridsB200Error", "boehm_refinement_matrix", "CapturedCalls", "set_adjoint_plans",
-    "adjoint_plans",
+    "adjoint_plans", "evaluate_autograd", "make_zero_",
 ]

@@ -114,6 +114,7 @@ extern "C" int sg_comm_destroy(sg_comm *comm)
 
 static int sg_allreduce(void *buf, int64_t count, int dtype, sg_comm *comm, void *stream)
 {
+    SG_NVTX("sg_allreduce_sum");
     SG_CHECK_ARG(buf && comm && count >= 0);
     SgNccl &n = sg_nccl();
     if (!n.ok) return SG_ERR_NCCL;

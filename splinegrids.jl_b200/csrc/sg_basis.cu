@@ -107,6 +107,7 @@ template <typename T, bool FUSED>
 static int sg_launch_basis(T *eval, int32_t *idx_out, const int32_t *idx_in, const T *knots, int64_t n_knots,
                            const T *samples, int64_t n, int p, int mdo, cudaStream_t st)
 {
+    SG_NVTX(FUSED ? "sg_dimension_build" : "sg_basis_tables");
     SG_CHECK_ARG(eval && knots && samples && n >= 1);
     SG_CHECK_ARG(FUSED ? idx_out != nullptr : idx_in != nullptr);
     if (p < 0 || p > SG_MAX_DEGREE) return SG_ERR_UNSUPPORTED;

@@ -19,6 +19,7 @@ static int sg_evaluate_impl(T *eval, int nin, const int64_t *n_samples, const in
                             const T *const *tables, const int32_t *const *indices, const int *degree,
                             const int *mdo, const int *der, const T *cp, const T *weights, void *stream)
 {
+    SG_NVTX("sg_evaluate");
     SG_CHECK_ARG(eval && cp);
     SgGridArgs<T> a;
     int rc = sg_fill_grid_args(a, nin, n_samples, n_cp, nout, tables, indices, degree, mdo, der);
@@ -45,6 +46,7 @@ static int sg_evaluate_multi_impl(T *const *evals, int n_der, const int *ders, i
                                   int nout, const T *const *tables, const int32_t *const *indices, const int *degree, const int *mdo,
                                   const T *cp, const T *weights, void *stream)
 {
+    SG_NVTX("sg_evaluate_multi");
     SG_CHECK_ARG(evals && ders && n_der >= 1 && cp);
     for (int q = 0; q < n_der; ++q) SG_CHECK_ARG(evals[q] != nullptr);
     cudaStream_t st = sg_stream(stream);
@@ -177,6 +179,7 @@ static int sg_evaluate_adjoint_impl(T *cp, int nin, const int64_t *n_samples, co
                                     const int *mdo, const int *der, const T *eval, const T *weights,
                                     void *workspace, size_t workspace_bytes, void *stream, const sg_adjoint_plan *plan = nullptr)
 {
+    SG_NVTX("sg_evaluate_adjoint");
     SG_CHECK_ARG(eval && cp);
     SgGridArgs<T> a;
     int rc = sg_fill_grid_args(a, nin, n_samples, n_cp, nout, tables, indices, degree, mdo, der);
@@ -271,6 +274,7 @@ static int sg_adjoint_plan_create_impl(sg_adjoint_plan **out, int nin, const int
                                        const T *const *tables, const int32_t *const *indices, const int *degree, const int *mdo,
                                        const int *der, int rational, void *stream)
 {
+    SG_NVTX("sg_adjoint_plan_create");
     SG_CHECK_ARG(out);
     *out = nullptr;
     SgGridArgs<T> a;

@@ -70,6 +70,7 @@ template <typename T>
 static int sg_exchange_push_impl(const T *grad, void *const *peer_stage, int world, int my_rank, int64_t plane_elems,
                                  int64_t c_last, int nout, int64_t k0, int64_t np, int64_t max_planes, void *stream)
 {
+    SG_NVTX("sg_exchange_push");
     SG_CHECK_ARG(grad && peer_stage && world >= 1 && my_rank >= 0 && my_rank < world && plane_elems >= 1 && nout >= 1);
     SG_CHECK_ARG(k0 >= 0 && np >= 0 && k0 + np <= c_last && np <= max_planes);
     if (world > SG_MAX_PEERS) return SG_ERR_UNSUPPORTED;
@@ -92,6 +93,7 @@ template <typename T>
 static int sg_exchange_reduce_impl(T *grad, const T *stage, int world, const int64_t *k0s, const int64_t *nps, int64_t plane_elems,
                                    int64_t c_last, int nout, int64_t max_planes, void *stream)
 {
+    SG_NVTX("sg_exchange_reduce");
     SG_CHECK_ARG(grad && stage && k0s && nps && world >= 1 && plane_elems >= 1 && c_last >= 1 && nout >= 1);
     if (world > SG_MAX_PEERS || c_last > 65535 || nout > 65535) return SG_ERR_UNSUPPORTED;
     SgSupports sup{};
@@ -256,6 +258,7 @@ static int sg_fill_flag_ptrs(SgFlagPtrs &pf, void *const *peer_flags, int world)
 
 extern "C" int sg_exchange_signal(void *const *peer_flags, int world, int my_rank, const void *local_sync, void *stream)
 {
+    SG_NVTX("sg_exchange_signal");
     SG_CHECK_ARG(peer_flags && local_sync && world >= 1 && my_rank >= 0 && my_rank < world);
     if (world > SG_MAX_PEERS) return SG_ERR_UNSUPPORTED;
     SgFlagPtrs pf{};
@@ -282,6 +285,7 @@ static int sg_exchange_wait_reduce_impl(T *grad, const T *stage, const void *my_
                                         int world, int my_rank, const int64_t *k0s, const int64_t *nps, int64_t plane_elems,
                                         int64_t c_last, int nout, int64_t max_planes, void *stream)
 {
+    SG_NVTX("sg_exchange_wait_reduce");
     SG_CHECK_ARG(grad && stage && my_flags && local_sync && k0s && nps && world >= 1 && plane_elems >= 1 && c_last >= 1 && nout >= 1);
     SG_CHECK_ARG(my_rank >= 0 && my_rank < world && reinterpret_cast<uintptr_t>(my_flags) % 8 == 0);
     if (world > SG_MAX_PEERS || c_last > 65535 || nout > 65535) return SG_ERR_UNSUPPORTED;

@@ -206,6 +206,7 @@ static int sg_fill_cp_strides(SgRefmatArgs<T> &a, int nin, const int64_t *n_cp)
                                        const int32_t *const *col_start, const T *const *nzval, const int64_t *nnz,   \
                                        void *stream)                                                                 \
     {                                                                                                                \
+        SG_NVTX("sg_refmat_mul");                                                                                    \
         SG_CHECK_ARG(Y && B);                                                                                        \
         SgRefmatArgs<T> a;                                                                                           \
         int rc = sg_fill_refmat<T>(a, ndims, sizeY, sizeB, n_ref, dims, row_ptr, col_start, nzval, nnz);             \
@@ -219,6 +220,7 @@ static int sg_fill_cp_strides(SgRefmatArgs<T> &a, int nin, const int64_t *n_cp)
                                                const int32_t *const *row_ptr, const int32_t *const *col_start,       \
                                                const T *const *nzval, const int64_t *nnz, void *stream)              \
     {                                                                                                                \
+        SG_NVTX("sg_refmat_mul_adjoint");                                                                            \
         SG_CHECK_ARG(Y && B);                                                                                        \
         SgRefmatArgs<T> a;                                                                                           \
         int rc = sg_fill_refmat<T>(a, ndims, sizeY, sizeB, n_ref, dims, row_ptr, col_start, nzval, nnz);             \
@@ -230,6 +232,7 @@ static int sg_fill_cp_strides(SgRefmatArgs<T> &a, int nin, const int64_t *n_cp)
     extern "C" int sg_scatter_active_##SUF(T *cp, int nin, const int64_t *n_cp, int nout, const int32_t *idx,        \
                                            const T *vals, int64_t n_active, void *stream)                            \
     {                                                                                                                \
+        SG_NVTX("sg_active_points");                                                                                 \
         SG_CHECK_ARG(cp && nout >= 1 && n_active >= 0);                                                              \
         if (n_active == 0) return SG_OK;                                                                             \
         SG_CHECK_ARG(idx && vals);                                                                                   \
@@ -244,6 +247,7 @@ static int sg_fill_cp_strides(SgRefmatArgs<T> &a, int nin, const int64_t *n_cp)
     extern "C" int sg_gather_zero_active_##SUF(T *vals, T *cp, int nin, const int64_t *n_cp, int nout,               \
                                                const int32_t *idx, int64_t n_active, void *stream)                   \
     {                                                                                                                \
+        SG_NVTX("sg_active_points");                                                                                 \
         SG_CHECK_ARG(cp && nout >= 1 && n_active >= 0);                                                              \
         if (n_active == 0) return SG_OK;                                                                             \
         SG_CHECK_ARG(idx && vals);                                                                                   \

@@ -984,6 +984,39 @@ def test_device_refinement_setup_kernels_vs_oracle(S, ft):
     assert np.array_equal(D.compact_flags(S.to_device(big), invert=True).cpu().numpy(), np.flatnonzero(big == 0).astype(np.int32))
 
 
+def test_ad_rules_match_reference_enzyme_test(S):
+    """Scope row f2.  test/test_EnzymeExt.jl:13-49 restated: loss(control_points_flat) = sum(evaluate!(grid; control_points));
+    reverse mode gives a non-zero gradient -- here checked exactly: it must equal the oracle's adjoint applied to ones,
+    the JVP must equal evaluate! on the tangent, and <J t, y> = <t, J' y>; make_zero! zeroes eval and the tables."""
+    from gpu_helpers import make_grid, oracle_adjoint, oracle_evaluate
+    grid, cp, w, rng = make_grid((10, 10), (2, 2), (50, 50), 2, "Float32", seed=1)
+    flat = torch.tensor(cp.ravel(order="F"), device="cuda", requires_grad=True)
+    loss = S.evaluate_autograd(grid, flat).sum()
+    loss.backward()
+    assert flat.grad is not None and bool((flat.grad != 0).any())              # the reference's assertion (:53)
+    gref = oracle_adjoint(grid, np.ones((50, 50, 2), dtype=np.float32, order="F"))
+    assert rel_err(flat.grad.cpu().numpy(), gref.ravel(order="F")) <= 1e-5
+    # a derivative order and Float64: gradient of a weighted sum, forward rule, dot-product identity
+    grid, cp, w, rng = make_grid((9, 7, 6), (3, 2, 2), (20, 18, 16), 2, "Float64", mdo=1, seed=2)
+    der = (0, 1, 0)
+    flat = torch.tensor(cp.ravel(order="F"), device="cuda", requires_grad=True)
+    y = np.asfortranarray(rng.random((20, 18, 16, 2)))
+    (S.evaluate_autograd(grid, flat, der) * S.to_device(y)).sum().backward()
+    assert rel_err(flat.grad.cpu().numpy(), oracle_adjoint(grid, y, der).ravel(order="F")) <= 1e-12
+    t = np.asfortranarray(rng.random(cp.shape))
+    import torch.autograd.forward_ad as fwAD
+    with fwAD.dual_level():
+        dual = fwAD.make_dual(flat.detach(), torch.tensor(t.ravel(order="F"), device="cuda"))
+        jt = fwAD.unpack_dual(S.evaluate_autograd(grid, dual, der)).tangent
+    ref_jt = oracle_evaluate(grid, t, der)
+    assert rel_err(S.to_numpy(jt), ref_jt) <= 1e-12
+    lhs = float((S.to_numpy(jt) * y).sum())
+    rhs = float((t * oracle_adjoint(grid, y, der)).sum())
+    assert abs(lhs - rhs) <= 1e-11 * abs(lhs)
+    S.make_zero_(grid)
+    assert float(grid.eval.abs().max()) == 0.0 and all(float(sd.eval.abs().max()) == 0.0 for sd in grid.spline_dimensions)
+
+
 def test_insert_and_collect_indices_kernels(S):
     """K11 `insert_kernel` (src/util_kernels.jl:69-79) and K12 `collect_indices_kernel` (:81-88)."""
     import ctypes as C
