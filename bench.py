@@ -544,6 +544,7 @@ def main_gpu(args):
                 "config": {"workload": w["name"], "step": "evaluate! + evaluate_adjoint! (+ NCCL all-reduce of the gradient for N>1)",
                            "sharding": f"sample grid in {world} slab(s) along axis 3, control points replicated",
                            "gradient_exchange": sh.exchange_kind, "exchange_check": exchange_check,
+                           "nvls_multicast_push": bool(sh.exchange is not None and any(sh.exchange.mc_ptrs)),
                            "launch": ("CUDA graph of the step's kernels (2 steps per replay)" if cap is not None
                                       else "eager" + (f" (graph capture failed: {cap_err})" if cap_err else "")),
                            "l2": "inputs/outputs (1.07 GB per op) exceed the 126 MB L2; no flush needed"},

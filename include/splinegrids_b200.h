@@ -172,7 +172,10 @@ int sg_evaluate_adjoint_f64(double *cp, int nin, const int64_t *n_samples, const
  * The plan captures the ARGUMENTS of sg_evaluate_adjoint (sizes, table / index pointers, derivative_order); it is valid
  * as long as those device arrays are unchanged -- re-create it after evaluate!(spline_dimension) (src/spline_dimension.jl:231)
  * or when derivative_order changes.  Results are identical to sg_evaluate_adjoint up to summation order.
- * peer_stage_or_null != NULL: fused gradient push as in sg_evaluate_adjoint_push below. */
+ * peer_stage_or_null != NULL: fused gradient push as in sg_evaluate_adjoint_push below.  multicast_stage_or_null != NULL: an
+ * NVLS multicast address that maps the staging buffers of ALL ranks (CUDA multicast object / symmetric-memory multicast
+ * pointer): the kernel then stores every finished control plane ONCE and the NVSwitch replicates it to every rank, so the
+ * sender's NVLink egress is 1/world of the peer-pointer loop (which stays the fallback when no multicast mapping exists). */
 typedef struct sg_adjoint_plan sg_adjoint_plan;
 int sg_adjoint_plan_create_f32(sg_adjoint_plan **plan, int nin, const int64_t *n_samples, const int64_t *n_cp, int nout,
                                const float *const *tables, const int32_t *const *indices, const int *degree,
@@ -186,10 +189,12 @@ int sg_adjoint_plan_destroy(sg_adjoint_plan *plan);
 int sg_adjoint_plan_info(const sg_adjoint_plan *plan, int *monotone, int *fused_tables_fit, int *rows2_max);
 int sg_evaluate_adjoint_planned_f32(const sg_adjoint_plan *plan, float *cp, const float *eval, const float *weights_or_null,
                                     void *workspace, size_t workspace_bytes, void *const *peer_stage_or_null, int world,
-                                    int my_rank, int64_t k0, int64_t np, int64_t max_planes, int keep_local, void *stream);
+                                    int my_rank, int64_t k0, int64_t np, int64_t max_planes, int keep_local,
+                                    void *multicast_stage_or_null, void *stream);
 int sg_evaluate_adjoint_planned_f64(const sg_adjoint_plan *plan, double *cp, const double *eval, const double *weights_or_null,
                                     void *workspace, size_t workspace_bytes, void *const *peer_stage_or_null, int world,
-                                    int my_rank, int64_t k0, int64_t np, int64_t max_planes, int keep_local, void *stream);
+                                    int my_rank, int64_t k0, int64_t np, int64_t max_planes, int keep_local,
+                                    void *multicast_stage_or_null, void *stream);
 
 /* ---- K5 refinement_matrix_array_mul_kernel -- src/refinement_matrix.jl:365-403, mult! :421-445
  * (row window helpers src/refinement_matrix.jl:103-125, src/utils.jl:204-235)

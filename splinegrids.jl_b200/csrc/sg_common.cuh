@@ -107,6 +107,8 @@ static inline int sg_fill_grid_args(SgGridArgs<T> &a, int nin, const int64_t *n_
 struct SgPushSpec {
     void *stage[SG_MAX_PEERS];   // staging buffer of every rank (peer-mapped), layout [world][nout][max_planes][plane_elems]
     int world, my_rank;          // world == 0: no push
+    int n_dst;                   // destinations the kernel stores to: `world` peer pointers, or 1 = stage[0] is a MULTICAST address
+                                 // (NVLS: one store, the NVSwitch replicates it into every rank's buffer -- 1/world of the egress)
     long long max_planes;
     int keep_local;              // 0: the caller does not need the local partial gradient (the reduce overwrites it): the fused
                                  // pipeline then skips its own writes of the control-point array (zeros and results)

@@ -350,13 +350,15 @@ static int sg_adjoint_push_impl(const sg_adjoint_plan *plan, T *cp, int nin, con
                                 const T *const *tables, const int32_t *const *indices, const int *degree, const int *mdo,
                                 const int *der, const T *eval, const T *weights, void *workspace, size_t workspace_bytes,
                                 void *const *peer_stage, int world, int my_rank, int64_t k0, int64_t np, int64_t max_planes,
-                                int keep_local, void *stream, PushFn push_fn)
+                                int keep_local, void *stream, PushFn push_fn, void *multicast_stage = nullptr)
 {
     if (!peer_stage || world < 1 || world > SG_MAX_PEERS || my_rank < 0 || my_rank >= world || nin < 1)
         return SG_ERR_INVALID_ARGUMENT;
     SgPushSpec spec{};
     for (int r = 0; r < world; ++r) spec.stage[r] = peer_stage[r];
     spec.world = world; spec.my_rank = my_rank; spec.max_planes = max_planes; spec.keep_local = keep_local;
+    spec.n_dst = world;
+    if (multicast_stage != nullptr) { spec.stage[0] = multicast_stage; spec.n_dst = 1; }   // one store reaches every rank
     g_sg_push = &spec; g_sg_push_done = false;
     int rc = sg_evaluate_adjoint_impl<T>(cp, nin, n_samples, n_cp, nout, tables, indices, degree, mdo, der, eval, weights,
                                          workspace, workspace_bytes, stream, plan);
@@ -416,7 +418,8 @@ static int sg_adjoint_push_impl(const sg_adjoint_plan *plan, T *cp, int nin, con
     extern "C" int sg_evaluate_adjoint_planned_##SUF(const sg_adjoint_plan *plan, T *cp, const T *eval,              \
                                                      const T *weights, void *workspace, size_t workspace_bytes,      \
                                                      void *const *peer_stage, int world, int my_rank, int64_t k0,    \
-                                                     int64_t np, int64_t max_planes, int keep_local, void *stream)   \
+                                                     int64_t np, int64_t max_planes, int keep_local,                 \
+                                                     void *multicast_stage, void *stream)                            \
     {                                                                                                                \
         if (!plan || plan->elem_size != (int)sizeof(T) || (plan->rational != (weights != nullptr)))                  \
             return SG_ERR_INVALID_ARGUMENT;                                                                          \
@@ -429,7 +432,7 @@ static int sg_adjoint_push_impl(const sg_adjoint_plan *plan, T *cp, int nin, con
         return sg_adjoint_push_impl<T>(plan, cp, plan->nin, plan->n_samples, plan->n_cp, plan->nout, tb,             \
                                        plan->indices, plan->degree, plan->mdo, plan->der, eval, weights, workspace,  \
                                        workspace_bytes, peer_stage, world, my_rank, k0, np, max_planes, keep_local,  \
-                                       stream, sg_exchange_push_##SUF);                                              \
+                                       stream, sg_exchange_push_##SUF, multicast_stage);                             \
     }
 
 SG_DEFINE_EVAL_API(float, f32)

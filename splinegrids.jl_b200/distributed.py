@@ -13,6 +13,8 @@ contiguous chunks, so the local output is simply a smaller dense array.
 """
 from __future__ import annotations
 
+import os
+
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -90,13 +92,16 @@ class PeerGradientExchange:
         self.dtype, self.device = last.dtype, last.device
         slot = self.nout * self.max_planes * self.plane_elems
         grp = dist.group.WORLD if group is None else group
-        self.stage, self.hdl, self.peer_ptrs = [], [], []
+        self.stage, self.hdl, self.peer_ptrs, self.mc_ptrs = [], [], [], []
         for _ in range(2):
             t = symm_mem.empty(world_size * slot, dtype=self.dtype, device=self.device)
             h = symm_mem.rendezvous(t, grp)
             self.stage.append(t)
             self.hdl.append(h)
             self.peer_ptrs.append((_lib.C.c_void_p * world_size)(*[int(x) for x in h.buffer_ptrs]))
+            # NVLS multicast mapping of the same buffers (0 when the fabric / driver has none): one store reaches all ranks
+            mc = int(getattr(h, "multicast_ptr", 0) or 0) if os.environ.get("SG_EXCHANGE_MULTICAST", "1") != "0" else 0
+            self.mc_ptrs.append(mc)
         # flag array (peer-mapped, one uint64 per rank) and the local exchange counter of the C ABI's own barrier
         self.flags = symm_mem.empty(max(world_size, 16), dtype=torch.int64, device=self.device)
         self.flags.zero_()
@@ -118,7 +123,8 @@ class PeerGradientExchange:
         from . import _lib
         b = self.step & 1
         self.step += 1
-        push = (b, self.peer_ptrs[b], self.world, self.rank, self.k0[self.rank], self.np_[self.rank], self.max_planes, 0)
+        push = (b, self.peer_ptrs[b], self.world, self.rank, self.k0[self.rank], self.np_[self.rank], self.max_planes, 0,
+                self.mc_ptrs[b])
         evaluate_adjoint_(grid, control_points=control_points, _push=push, **kw)
         return self._wait_reduce_(control_points, b, _lib.stream_ptr(self.device))
 

@@ -181,9 +181,9 @@ for (Tv, suf) in ((Float32, "f32"), (Float64, "f64"))
         GC.@preserve plan cp eval workspace begin
             check(ccall(($(sym("sg_evaluate_adjoint_planned")), LIB), Cint,
                         (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}, Cint, Cint, Int64, Int64, Int64,
-                         Cint, Ptr{Cvoid}),
+                         Cint, Ptr{Cvoid}, Ptr{Cvoid}),
                         plan.handle, devptr(cp), devptr(eval), C_NULL, devptr(workspace), length(workspace), C_NULL, 0, 0, 0, 0, 0, 1,
-                        stream_ptr()), "sg_evaluate_adjoint_planned")
+                        C_NULL, stream_ptr()), "sg_evaluate_adjoint_planned")
             CUDA.synchronize()
         end
         return nothing
@@ -240,13 +240,14 @@ end
 # peer_stage / peer_flags: the ranks' staging buffers and flag arrays mapped into this process (CUDA IPC or CUDA.jl peer access),
 # my_flags / local_sync: this rank's own flag array (world x UInt64, zeroed once) and 64 bytes of local device memory (zeroed once).
 function adjoint_push!(plan::AdjointPlan, cp::CuArray{Float64}, eval::CuArray{Float64}, workspace::CuVector{UInt8},
-        peer_stage::Vector{Ptr{Cvoid}}, my_rank::Integer, k0::Integer, np::Integer, max_planes::Integer; keep_local::Bool = false)
+        peer_stage::Vector{Ptr{Cvoid}}, my_rank::Integer, k0::Integer, np::Integer, max_planes::Integer; keep_local::Bool = false,
+        multicast_stage::Ptr{Cvoid} = C_NULL)   # NVLS multicast address of the staging buffers (CUDA.jl: cuMulticast* mapping)
     GC.@preserve plan cp eval workspace peer_stage begin
         check(ccall((:sg_evaluate_adjoint_planned_f64, LIB), Cint,
                     (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Ptr{Ptr{Cvoid}}, Cint, Cint, Int64, Int64, Int64,
-                     Cint, Ptr{Cvoid}),
+                     Cint, Ptr{Cvoid}, Ptr{Cvoid}),
                     plan.handle, devptr(cp), devptr(eval), C_NULL, devptr(workspace), length(workspace), peer_stage, length(peer_stage),
-                    my_rank, k0, np, max_planes, keep_local, stream_ptr()), "sg_evaluate_adjoint_planned (push)")
+                    my_rank, k0, np, max_planes, keep_local, multicast_stage, stream_ptr()), "sg_evaluate_adjoint_planned (push)")
     end
 end
 function exchange_wait_reduce!(grad::CuArray{Float64}, my_stage::CuArray{Float64}, my_flags::CuVector{UInt64}, local_sync::CuVector{UInt8},

@@ -284,7 +284,8 @@ def evaluate_adjoint_(obj, *, derivative_order: Optional[Sequence[int]] = None, 
             fn = getattr(_lib.lib(), "sg_evaluate_adjoint_planned_" + _lib.suffix(grid.dtype))
             args = (plan.handle, _lib.ptr(cp), _lib.ptr(eval_), _lib.ptr(grid.weights), _lib.ptr(ws), C.c_size_t(ws.numel()))
             if _push is None:
-                args = args + (C.c_void_p(0), C.c_int(0), C.c_int(0), C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int(1))
+                args = args + (C.c_void_p(0), C.c_int(0), C.c_int(0), C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int(1),
+                               C.c_void_p(0))
         else:
             args = (_lib.ptr(cp), *_grid_call_args(grid, der), _lib.ptr(eval_), _lib.ptr(grid.weights), _lib.ptr(ws),
                     C.c_size_t(ws.numel()))
@@ -294,6 +295,8 @@ def evaluate_adjoint_(obj, *, derivative_order: Optional[Sequence[int]] = None, 
             keep_local = _push[7] if len(_push) > 7 else 1
             args = args + (peer_ptrs, C.c_int(world), C.c_int(rank), C.c_int64(k0), C.c_int64(np_), C.c_int64(max_planes),
                            C.c_int(keep_local))
+            if plan is not None:                       # NVLS multicast address of the staging buffers (0: none)
+                args = args + (C.c_void_p(_push[8] if len(_push) > 8 else 0),)
         prep = (fn, args, grid.device.index, ws, plan)
         _prepared_store(grid, key, prep)
     fn, args, dev_index = prep[0], prep[1], prep[2]
