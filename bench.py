@@ -426,7 +426,7 @@ def main_gpu(args):
                              "frac_of_hbm_roofline": nb_local / (ms_adj * 1e-3) / 1e9 / hbm,
                              "note": "local kernels only (no all-reduce)"},
     }
-    # dominant kernel of the step (49 % of it, profiles/r01_ncu_launch_shares.txt): the TMA-fed double march of the
+    # dominant kernel of the step (~42 % of it, profiles/r02_ncu_launches_bench_step.csv): the TMA-fed double march of the
     # adjoint.  Its launch duration is measured live with CUDA events recorded by the library on the launch stream
     # right before / after the kernel (sg_profile_adjoint_main, include/splinegrids_b200.h).
     ms_main = None
@@ -450,14 +450,14 @@ def main_gpu(args):
                 "bound": "hbm", "achieved": ops["evaluate"]["achieved_GBs"], "peak": hbm, "unit": "GB/s",
                 "frac": ops["evaluate"]["frac_of_hbm_roofline"], "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                 "algorithmic_bytes_per_launch": nb_local, "traffic": args.traffic_bytes,
-                "traffic_source": "profiles/r01_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, "
+                "traffic_source": "profiles/r02_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, "
                                   "N=1 full grid)" if args.traffic_bytes else None}
     if ms_main is not None:
         # algorithmic bytes of this launch: the sample array read once + the tables/indices (SURVEY 8d's adjoint
         # figure minus the control-point write, which the post kernel does)
         nb_main = nb_local - int(np.prod(w["n_cp"])) * w["nout"] * 8
         tr_main = None
-        tp = ROOT / "profiles" / "r01_traffic.json"
+        tp = ROOT / "profiles" / "r02_traffic.json"
         if tp.exists() and world == 1:
             k = json.loads(tp.read_text()).get("adjoint", {}).get("sg_adj_march2_tma_kernel")
             if k:
@@ -468,8 +468,8 @@ def main_gpu(args):
                     "achieved": nb_main / (ms_main * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                     "frac": nb_main / (ms_main * 1e-3) / 1e9 / hbm, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                     "launch_ms": ms_main, "algorithmic_bytes_per_launch": nb_main, "traffic": tr_main,
-                    "traffic_source": "profiles/r01_traffic.json (ncu --set full, N=1 full grid; includes the 135 MB of tile/chunk "
-                                      "partials the kernel writes)" if tr_main else None,
+                    "traffic_source": "profiles/r02_traffic.json (ncu --set full at HEAD, N=1 full grid: the sample array read once + the "
+                                      "part of the 135 MB of evict-last partials that reaches HBM before the kernel ends)" if tr_main else None,
                     "timing": "CUDA events recorded by the library on the launch stream around this kernel",
                     "also": {"evaluate_adjoint_op_frac": ops["evaluate_adjoint"]["frac_of_hbm_roofline"],
                              "evaluate_kernel": fwd_roof}}
@@ -575,7 +575,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.traffic_bytes is None:     # DRAM traffic of the roofline kernel from the committed ncu capture
-        tp = ROOT / "profiles" / "r01_traffic.json"
+        tp = ROOT / "profiles" / "r02_traffic.json"
         if tp.exists():
             args.traffic_bytes = float(json.loads(tp.read_text())["total"])
     if args.impl == "reference":
