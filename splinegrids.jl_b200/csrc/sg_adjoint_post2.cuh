@@ -20,13 +20,17 @@
 #define SG_POST2_RMAX 20          // gather weights kept in registers per control index
 #define SG_POST2_PITCH (SG_POST2_JMAX + SG_POST2_JMAX / 4 + 4)   // skewed row: sample jj lives at jj + (jj >> 2)
 
+__device__ __forceinline__ void sg_discard_l2(const void *p)
+{
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+}
 // grid = ((tiles2 + 1) * ceil(c1 / 128), c3, nout); requires G2 >= P (only neighbouring tiles overlap)
 template <typename T, int P, int G2>
 __global__ void __launch_bounds__(128, 5) sg_adj_post2_kernel(T *__restrict__ cp, const T *__restrict__ Pp, const T *__restrict__ table1,
                                                            const int32_t *__restrict__ index1, const int32_t *__restrict__ g_lo,
                                                            const T *__restrict__ g_w, const SgAdjointHeader *hdr, int64_t n1, int64_t c1, int64_t c2, int64_t c3, int P1,
                                                            int tiles2, int G3, int chunks3, int path,
-                                                           const __grid_constant__ SgPushSpec push)
+                                                           const __grid_constant__ SgPushSpec push, int discard)
 {
     constexpr int S = G2 + P;
     constexpr int JMAX = SG_POST2_JMAX;
@@ -125,6 +129,30 @@ __global__ void __launch_bounds__(128, 5) sg_adj_post2_kernel(T *__restrict__ cp
                     T v = ra[q] + sa[q];
                     if (q < P) v += rb[q] + sb[q];
                     rows[q][js] = v;
+                }
+                if (discard) {
+                    // Every partial is read exactly once, here.  Its cache line is still dirty in L2 (the march kernel stored
+                    // it with evict-last): discard it instead of letting the next march's stores push 135 MB of dead data
+                    // out to HBM.  All lanes of the warp have consumed their loads once their shared-memory stores above
+                    // are issued, so one lane per 128-byte line (16 / 32 consecutive columns) drops it.
+                    __syncwarp();
+                    constexpr int LINE = 128 / (int)sizeof(T);
+                    if (((jc + jj) % LINE) == 0 && jj + LINE <= len) {
+#pragma unroll
+                        for (int q = 0; q < G2; ++q) {
+                            if (own_c) {
+                                sg_discard_l2(p0 + n1 * q);
+                                if (two_c) sg_discard_l2(p1 + n1 * q);
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < P; ++q) {
+                            if (prev_c) {
+                                sg_discard_l2(p0 - n1 * (S - G2 - q));
+                                if (two_c) sg_discard_l2(p1 - n1 * (S - G2 - q));
+                            }
+                        }
+                    }
                 }
             }
         };
