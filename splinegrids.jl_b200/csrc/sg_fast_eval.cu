@@ -2,6 +2,7 @@
 #include <cstdlib>
 
 #include <algorithm>
+#include <cmath>
 #include <type_traits>
 
 #include "sg_evaluate_generic.cuh"
@@ -69,13 +70,47 @@ static bool sg_make_cp_tensor_map(CUtensorMap &tm, const T *cp, const SgGridArgs
                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Chunk of the marching axis from the kernel's RESIDENT capacity: full waves, with a preference for long chunks (a CTA pays
+// ~8 planes' worth of start-up: window load + first window contraction).  Measured on the 8-way slab of C3 (64 planes, 256
+// column tiles, capacity 296): one chunk of 64 planes 0.0315 ms, two of 32 (512 CTAs = 1.7 waves) 0.0356 ms.
+static int sg_pick_chunk_waves(int64_t n_march, int64_t col_tiles, int64_t capacity, int max_chunk)
+{
+    int best = (int)std::min<int64_t>(n_march, max_chunk);
+    double best_score = -1.0;
+    for (int64_t nch = 1; nch <= std::min<int64_t>(n_march, 64); ++nch) {
+        int64_t chunk = (n_march + nch - 1) / nch;
+        chunk = (chunk + 7) / 8 * 8;
+        if (chunk > max_chunk) continue;
+        const int64_t ne = (n_march + chunk - 1) / chunk;
+        const double ctas = (double)col_tiles * ne, waves = std::ceil(ctas / (double)capacity);
+        const double score = ctas / (waves * capacity) * (double)chunk / ((double)chunk + 8.0);
+        if (score > best_score) { best_score = score; best = (int)chunk; }
+    }
+    return best;
+}
+
 template <typename T, int P, int V1, int V2, int TY>
 static int sg_launch_eval3d(T *eval, const SgGridArgs<T> &a, const T *cp, cudaStream_t st)
 {
     const int64_t gx = (a.n_samples[0] + 32 * V1 - 1) / (32 * V1);
     const int64_t gy = (a.n_samples[1] + TY * V2 - 1) / (TY * V2);
     // (the TMA variant stages at most SG_TMA_B3 control planes per CTA: a finer cut of the marching axis suits it)
-    const int chunk = sg_pick_chunk(a.n_samples[2], gx * gy, 32, 1024, sg_env_int("SG_CHUNK3D", 0), 148 * 14);
+    int chunk = sg_pick_chunk(a.n_samples[2], gx * gy, 32, 1024, sg_env_int("SG_CHUNK3D", 0), 148 * 14);
+    if (sg_env_int("SG_CHUNK3D", 0) == 0 && sg_env_int("SG_EVAL_WAVES", 1)) {
+        static const int64_t capacity = [] {
+            int per_sm = 0, dev = 0, sms = 148;
+            auto kern = sg_eval3d_march_kernel<T, P, V1, V2, TY, true>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            const size_t smem = sizeof(T) * SG_TMA_B1 * SG_TMA_B2 * SG_TMA_B3 + 64 * ((P + 1) * sizeof(T) + sizeof(int)) + 32;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * TY, smem) != cudaSuccess || per_sm < 1) {
+                cudaGetLastError();
+                return (int64_t)0;
+            }
+            if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            return (int64_t)per_sm * sms;
+        }();
+        if (capacity > 0) chunk = sg_pick_chunk_waves(a.n_samples[2], gx * gy, capacity, 96);
+    }
     const int64_t gz = (a.n_samples[2] + chunk - 1) / chunk;
     if (gy > 65535 || gz > 65535) return SG_ERR_UNSUPPORTED;
     const bool vec_ok = (reinterpret_cast<uintptr_t>(eval) % 16 == 0) && (a.n_samples[0] % V1 == 0);
