@@ -369,11 +369,33 @@ static SgMarch2Plan sg_adjoint_march2_plan(int nin, const int64_t *n_samples, co
     mp.G2 = SG_M2_G2;
     const int64_t nsp2 = n_cp[1] - P, nsp3 = n_cp[2] - P;
     mp.tiles2 = (int)((nsp2 + mp.G2 - 1) / mp.G2);
-    // The number of chunks of dimension 3 is a CTA-count target (~2.9 waves of 3 CTAs x 148 SMs measured best on C3:
-    // long CTAs amortise the pipeline fill); the chunks adapt on device to the spans that hold samples
-    // (sg_m2_chunk_len), G3 is their worst-case length = the row stride of the partials.
+    // The number of chunks of dimension 3 sets the CTA count.  The march kernel keeps 3 CTAs per SM resident (launch bounds
+    // and shared memory), and what pays is ONE full wave of long CTAs: fewer pipeline fills, fewer chunk halos in the
+    // partials (C3: 3 chunks = 384 CTAs 0.227 ms, 10 chunks = 1280 CTAs 0.232 ms, 4 chunks = 512 CTAs = 1.15 waves 0.283 ms;
+    // 8-way slab 0.045 vs 0.050 ms).  The chunks adapt on device to the spans that hold samples (sg_m2_chunk_len), G3 is their
+    // worst-case length = the row stride of the partials.
     const int64_t base = ((n_samples[0] + 127) / 128) * mp.tiles2 * nout;
-    int64_t chunks = std::max<int64_t>(1, (sg_env_int("SG_ADJ_M2_CTAS", 1280) + base / 2) / base);
+    static const int64_t capacity = [] {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        return (int64_t)3 * sms;
+    }();
+    int64_t chunks = 1;
+    {
+        const int target = sg_env_int("SG_ADJ_M2_CTAS", 0);
+        if (target > 0) {
+            chunks = std::max<int64_t>(1, (target + base / 2) / base);
+        } else {
+            double best_score = -1.0;
+            for (int64_t nch = 1; nch <= std::max<int64_t>(1, nsp3 / std::max(2, P)); ++nch) {
+                const int64_t G = (nsp3 + nch - 1) / nch;
+                if ((nsp3 + G - 1) / G != nch) continue;
+                const double ctas = (double)base * nch, waves = std::ceil(ctas / (double)capacity);
+                const double score = ctas / (waves * capacity) * (double)G / ((double)G + P);
+                if (score > best_score) { best_score = score; chunks = nch; }
+            }
+        }
+    }
     const int forced = sg_env_int("SG_ADJ_M2_G3", 0);
     if (forced > 0) chunks = (nsp3 + forced - 1) / forced;
     chunks = std::min<int64_t>(chunks, std::max<int64_t>(1, nsp3 / std::max(2, P)));
