@@ -24,6 +24,11 @@
 
 #define SG_ADJ_PIECE 64   // marching steps staged in shared memory at a time
 
+// reciprocal of the rational denominator: correctly rounded for both types; the Float32 one is MUFU.RCP + one refinement
+// instead of the full IEEE division sequence
+__device__ __forceinline__ float sg_recip(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ double sg_recip(double x) { return 1.0 / x; }
+
 // All fast kernels return at their first instruction when the prep kernel flagged non-monotone span indices (the atomic
 // scatter kernel then does the work) -- no host synchronisation.
 enum { SG_PATH_MULTIPASS = 0 };
@@ -260,7 +265,7 @@ __global__ void __launch_bounds__(128) sg_adj_march_kernel(const __grid_constant
                 T den = b[0] * Tw[v][0];
 #pragma unroll
                 for (int k = 1; k <= P; ++k) den = fma(b[k], Tw[v][k], den);
-                const T inv = T(1) / den;
+                const T inv = sg_recip(den);
 #pragma unroll
                 for (int t = 0; t < NT; ++t) x[t][v] *= inv;
             }
