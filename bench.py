@@ -33,16 +33,29 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-WORKLOAD = dict(name="C3: 3-D cubic volume, control 128^3, samples 512^3, Nout=1, Float64",
-                n_cp=(128, 128, 128), degree=(3, 3, 3), n_samples=(512, 512, 512), nout=1, float_type="Float64")
+WORKLOADS = {
+    # BASELINE.json configs.  C3 is the one the metric is quoted on: the default and the only one the
+    # driver runs; the others (N = 1 only, `--config`) give one line per config for profiles/.
+    "C1": dict(name="C1: README 3-D grid, control (10,10,5), degree (2,3,2), samples (50,50,25), Nout=4, Float64",
+               n_cp=(10, 10, 5), degree=(2, 3, 2), n_samples=(50, 50, 25), nout=4, float_type="Float64"),
+    "C2": dict(name="C2: 2-D cubic surface, control 64x64, samples 4096x4096, Nout=3, Float32",
+               n_cp=(64, 64), degree=(3, 3), n_samples=(4096, 4096), nout=3, float_type="Float32"),
+    "C3": dict(name="C3: 3-D cubic volume, control 128^3, samples 512^3, Nout=1, Float64",
+               n_cp=(128, 128, 128), degree=(3, 3, 3), n_samples=(512, 512, 512), nout=1, float_type="Float64"),
+    "C4": dict(name="C4: 2-D NURBS surface, control 256x256 with random weights, samples 8192x8192, Nout=3, Float32 "
+                    "(adjoint = this package's extension: transpose of the fixed-weights rational map)",
+               n_cp=(256, 256), degree=(3, 3), n_samples=(8192, 8192), nout=3, float_type="Float32", nurbs=True),
+}
+WORKLOAD = WORKLOADS["C3"]
 METRIC = "evaluate!+evaluate_adjoint! sample-values/sec"
 UNIT = "sample-values/s"
 
 
-def algorithmic_bytes(n_samples, n_cp, degree, nout, elem=8):
-    """output (or adjoint input) + control points + selected table slices + span indices."""
+def algorithmic_bytes(n_samples, n_cp, degree, nout, elem=8, nurbs=False):
+    """output (or adjoint input) + control points (+ weights) + selected table slices + span indices."""
     n, c = int(np.prod(n_samples)), int(np.prod(n_cp))
-    return n * nout * elem + c * nout * elem + sum(nd * ((p + 1) * elem + 4) for nd, p in zip(n_samples, degree))
+    return (n * nout * elem + c * nout * elem + (c * elem if nurbs else 0) +
+            sum(nd * ((p + 1) * elem + 4) for nd, p in zip(n_samples, degree)))
 
 
 def load_peaks():
@@ -132,7 +145,7 @@ def cpu_reference_setup(planes: int):
     from oracle import oracle_c as OC
     from oracle import oracle_np as O
     w = WORKLOAD
-    npdt = np.float64
+    npdt = np.float64 if w["float_type"] == "Float64" else np.float32
     dims = []
     for d, (c, p, n) in enumerate(zip(w["n_cp"], w["degree"], w["n_samples"])):
         kv, mu, ka = O.clamped_knot_vector(c, p, npdt)
@@ -142,16 +155,18 @@ def cpu_reference_setup(planes: int):
         idx = OC.span_indices(sp, ka, p)
         dims.append((OC.basis_tables(ka, sp, idx, p, 0), idx))
     rng = np.random.default_rng(1)
-    cp = np.asfortranarray(rng.random(w["n_cp"] + (w["nout"],)))
+    cp = np.asfortranarray(rng.random(w["n_cp"] + (w["nout"],)).astype(npdt))
+    wts = np.asfortranarray((0.5 + np.random.default_rng(2).random(w["n_cp"])).astype(npdt)) if w.get("nurbs") else None
     n_s = w["n_samples"][:-1] + (planes,)
-    e_in = np.asfortranarray(np.random.default_rng(3).random(n_s + (w["nout"],)))
+    e_in = np.asfortranarray(np.random.default_rng(3).random(n_s + (w["nout"],)).astype(npdt))
     out = np.empty(n_s + (w["nout"],), dtype=npdt, order="F")
     g = np.empty(w["n_cp"] + (w["nout"],), dtype=npdt, order="F")
     tabs, idxs = [t for t, _ in dims], [i for _, i in dims]
+    der0 = [0] * len(w["n_cp"])
 
     def step():
-        OC.evaluate(tabs, idxs, w["degree"], [0, 0, 0], cp, None, out)
-        OC.evaluate_adjoint(tabs, idxs, w["degree"], [0, 0, 0], e_in, g.shape, None, g)
+        OC.evaluate(tabs, idxs, w["degree"], der0, cp, wts, out)
+        OC.evaluate_adjoint(tabs, idxs, w["degree"], der0, e_in, g.shape, wts, g)
 
     values = 2 * int(np.prod(n_s)) * w["nout"]
     return step, values, OC.max_threads()
@@ -195,15 +210,15 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    planes = args.cpu_planes
+    planes = min(args.cpu_planes, WORKLOAD["n_samples"][-1])
     warmup = max(1, args.warmup)
     # as many of the requested steps as fit ~150 s of CPU time (one step of the 32-plane sample takes ~0.5 s)
     value, dt, cores, steps = run_cpu_reference(args.steps, warmup, planes, budget_s=150.0)
-    sample = (f"slab of {planes}/512 planes of the C3 grid (512x512x{planes} samples, all 128^3 control points), "
-              f"evaluate!+adjoint, C/OpenMP restatement of the reference algorithm (Julia unavailable), {cores} threads")
+    sample = (f"slab of {planes}/{WORKLOAD['n_samples'][-1]} rows along the slowest axis of the {args.config} grid (all control "
+              f"points), evaluate!+adjoint, C/OpenMP restatement of the reference algorithm (Julia unavailable), {cores} threads")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f64" if WORKLOAD["float_type"] == "Float64" else "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD["name"], "cpu_sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -311,8 +326,15 @@ def main_gpu(args):
     S.set_synchronous(False)                       # the benchmark synchronises once per timed region
     gdims = tuple(S.SplineDimension(c, p, n, float_type=w["float_type"])
                   for c, p, n in zip(w["n_cp"], w["degree"], w["n_samples"]))
-    sh = S.SlabShardedGrid(gdims, w["nout"], rank, world, peer_exchange=(world > 1 and not args.nccl_allreduce))
+    nurbs = bool(w.get("nurbs"))
+    akw = {"allow_nurbs": True} if nurbs else {}
+    elem = 8 if w["float_type"] == "Float64" else 4
+    sh = S.SlabShardedGrid(gdims, w["nout"], rank, world, nurbs=nurbs, peer_exchange=(world > 1 and not args.nccl_allreduce))
     grid = sh.local
+    if nurbs:
+        gw = torch.Generator(device=dev)
+        gw.manual_seed(2)
+        grid.weights.copy_(0.5 + torch.rand(grid.weights.shape, dtype=grid.weights.dtype, device=dev, generator=gw))
     n_local = tuple(grid.eval.shape[:-1])
     gen = torch.Generator(device=dev)
     gen.manual_seed(1)
@@ -331,7 +353,7 @@ def main_gpu(args):
 
     def step():
         S.evaluate_(grid)
-        sh.evaluate_adjoint_(eval=e_in, control_points=grad)          # local adjoint + NCCL all-reduce (N > 1)
+        sh.evaluate_adjoint_(eval=e_in, control_points=grad, **akw)   # local adjoint + gradient exchange (N > 1)
 
     values_per_step = 2 * int(np.prod(w["n_samples"])) * w["nout"]      # whole job, both ops
     exchange_check = None
@@ -412,11 +434,11 @@ def main_gpu(args):
     reps = max(3, min(args.steps, 10))
     ms_fwd = time_fn(lambda: S.evaluate_(grid), reps)
     var_fwd = S.last_variant()
-    ms_adj = time_fn(lambda: S.evaluate_adjoint_(grid, eval=e_in, control_points=grad), reps)
+    ms_adj = time_fn(lambda: S.evaluate_adjoint_(grid, eval=e_in, control_points=grad, **akw), reps)
     var_adj = S.last_variant()
     peaks, peak_kind = load_peaks()
     hbm = float(peaks["hbm_gbs"])
-    nb_local = algorithmic_bytes(n_local, w["n_cp"], w["degree"], w["nout"])
+    nb_local = algorithmic_bytes(n_local, w["n_cp"], w["degree"], w["nout"], elem, nurbs)
     n_local_values = int(np.prod(n_local)) * w["nout"]
     ops = {
         "evaluate": {"ms": ms_fwd, "values_per_s": n_local_values / (ms_fwd * 1e-3), "variant": var_fwd,
@@ -435,7 +457,7 @@ def main_gpu(args):
         lib.sg_profile_adjoint_main(1)
         samples = []
         for _ in range(reps):
-            S.evaluate_adjoint_(grid, eval=e_in, control_points=grad)
+            S.evaluate_adjoint_(grid, eval=e_in, control_points=grad, **akw)
             t = float(lib.sg_profile_adjoint_main_ms())
             if t > 0:
                 samples.append(t)
@@ -444,18 +466,18 @@ def main_gpu(args):
             ms_main = float(np.mean(samples))
     # roofline kernel = the forward march kernel (ONE launch == the whole evaluate! call, so its CUDA-event time is
     # the kernel's launch duration).  The adjoint is a chain of kernels; its op-level fraction is in "also"/"ops".
-    fwd_roof = {"kernel": f"sg_eval3d_march_kernel<double,3,2,4,4,TMA={'true' if var_fwd.endswith('tma') else 'false'}> "
-                          f"[{var_fwd}] (evaluate!, one launch per call)",
+    fwd_roof = {"kernel": (f"sg_eval3d_march_kernel<double,3,2,4,4,TMA={'true' if var_fwd.endswith('tma') else 'false'}> "
+                           if args.config == "C3" else "") + f"[{var_fwd}] (evaluate!, one launch per call)",
                 "share_of_step": ms_fwd / (ms_fwd + ms_adj),
                 "bound": "hbm", "achieved": ops["evaluate"]["achieved_GBs"], "peak": hbm, "unit": "GB/s",
                 "frac": ops["evaluate"]["frac_of_hbm_roofline"], "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
-                "algorithmic_bytes_per_launch": nb_local, "traffic": args.traffic_bytes,
+                "algorithmic_bytes_per_launch": nb_local, "traffic": args.traffic_bytes if args.config == "C3" else None,
                 "traffic_source": "profiles/r02_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, "
                                   "N=1 full grid)" if args.traffic_bytes else None}
     if ms_main is not None:
         # algorithmic bytes of this launch: the sample array read once + the tables/indices (SURVEY 8d's adjoint
         # figure minus the control-point write, which the post kernel does)
-        nb_main = nb_local - int(np.prod(w["n_cp"])) * w["nout"] * 8
+        nb_main = nb_local - int(np.prod(w["n_cp"])) * w["nout"] * elem
         tr_main = None
         tp = ROOT / "profiles" / "r02_traffic.json"
         if tp.exists() and world == 1:
@@ -501,7 +523,7 @@ def main_gpu(args):
         S.evaluate_(grid)
         ev_fwd.record(s_main)
         s_main.wait_event(ev_ein)
-        sh.evaluate_adjoint_(eval=e_in, control_points=grad)    # (+ gradient exchange for N > 1)
+        sh.evaluate_adjoint_(eval=e_in, control_points=grad, **akw)    # (+ gradient exchange for N > 1)
         ev_adj.record(s_main)
         with torch.cuda.stream(s_down):
             s_down.wait_event(ev_fwd)
@@ -522,7 +544,6 @@ def main_gpu(args):
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-    elem = cp.element_size()
     e2e = {"value": values_per_step / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": e2e_steps,
            "h2d_bytes_per_step": int((cp.numel() + e_in.numel()) * elem),
            "d2h_bytes_per_step": int((grid.eval.numel() + cp.numel()) * elem),
@@ -532,22 +553,24 @@ def main_gpu(args):
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, dts, cores, _ = run_cpu_reference(steps=8, warmup=1, planes=args.cpu_planes, budget_s=15.0)
+        cpl = min(args.cpu_planes, w["n_samples"][-1])
+        v, dts, cores, _ = run_cpu_reference(steps=8, warmup=1, planes=cpl, budget_s=15.0)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step_sample": dts * 1e3,
-               "sample": f"slab of {args.cpu_planes}/512 planes of the same grid, evaluate!+adjoint, C/OpenMP restatement "
+               "sample": f"slab of {cpl}/{w['n_samples'][-1]} rows along the slowest axis of the same grid, evaluate!+adjoint, C/OpenMP restatement "
                          f"of the reference algorithm (Julia not installed, the reference package cannot run)"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "vs_baseline": None, "dtype": "f64" if elem == 8 else "f32", "data": "synthetic",
                 "config": {"workload": w["name"], "step": "evaluate! + evaluate_adjoint! (+ NCCL all-reduce of the gradient for N>1)",
                            "sharding": f"sample grid in {world} slab(s) along axis 3, control points replicated",
                            "gradient_exchange": sh.exchange_kind, "exchange_check": exchange_check,
                            "nvls_multicast_push": bool(sh.exchange is not None and any(sh.exchange.mc_ptrs)),
                            "launch": ("CUDA graph of the step's kernels (2 steps per replay)" if cap is not None
                                       else "eager" + (f" (graph capture failed: {cap_err})" if cap_err else "")),
-                           "l2": "inputs/outputs (1.07 GB per op) exceed the 126 MB L2; no flush needed"},
+                           "l2": (f"inputs/outputs ({nb_local / 1e9:.2f} GB per op) exceed the 126 MB L2; no flush needed" if nb_local > 150e6
+                                  else "working set fits the 126 MB L2: warm-cache numbers (launch-latency regime)")},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "ops": ops,
                 "cpu_baseline": cpu}
         sys.stdout.flush()
@@ -563,6 +586,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C3", choices=sorted(WORKLOADS), help="BASELINE config (default C3, the one the metric is "
+                    "quoted on; the others run at N = 1 only and give one line per config for profiles/)")
     ap.add_argument("--cpu-planes", type=int, default=32, help="slab thickness of the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -573,6 +598,11 @@ def main():
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/)")
     args = ap.parse_args()
+    if args.config != "C3":
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            ap.error("--config other than C3 runs at N = 1 only")
+        global WORKLOAD
+        WORKLOAD = WORKLOADS[args.config]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.traffic_bytes is None:     # DRAM traffic of the roofline kernel from the committed ncu capture
         tp = ROOT / "profiles" / "r02_traffic.json"
