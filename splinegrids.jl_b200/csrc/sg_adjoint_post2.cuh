@@ -26,7 +26,7 @@ __device__ __forceinline__ void sg_discard_l2(const void *p)
 }
 // grid = ((tiles2 + 1) * ceil(c1 / 128), c3, nout); requires G2 >= P (only neighbouring tiles overlap)
 template <typename T, int P, int G2>
-__global__ void __launch_bounds__(128, 5) sg_adj_post2_kernel(T *__restrict__ cp, const T *__restrict__ Pp, const T *__restrict__ table1,
+__global__ void __launch_bounds__(128, 4) sg_adj_post2_kernel(T *__restrict__ cp, const T *__restrict__ Pp, const T *__restrict__ table1,
                                                            const int32_t *__restrict__ index1, const int32_t *__restrict__ g_lo,
                                                            const T *__restrict__ g_w, const SgAdjointHeader *hdr, int64_t n1, int64_t c1, int64_t c2, int64_t c3, int P1,
                                                            int tiles2, int G3, int chunks3, int path,
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(128, 5) sg_adj_post2_kernel(T *__restrict__ cp
         // constants inside each instantiation): 2 columns x up to 2 chunks x (G2 + P) rows in flight per thread.
         auto load_piece = [&](auto OWN, auto PREV, auto TWO) {
             constexpr bool own_c = decltype(OWN)::value, prev_c = decltype(PREV)::value, two_c = decltype(TWO)::value;
-#pragma unroll 2
+#pragma unroll 4
             for (int jj = tid; jj < len; jj += 128) {
                 const T *__restrict__ p0 = Pp + jc + jj + off0;
                 const T *__restrict__ p1 = Pp + jc + jj + off1;
