@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(128, 4) sg_adj_post2_kernel(T *__restrict__ cp
                                                            const int32_t *__restrict__ index1, const int32_t *__restrict__ g_lo,
                                                            const T *__restrict__ g_w, const SgAdjointHeader *hdr, int64_t n1, int64_t c1, int64_t c2, int64_t c3, int P1,
                                                            int tiles2, int G3, int chunks3, int path,
-                                                           const __grid_constant__ SgPushSpec push, int discard)
+                                                           const __grid_constant__ SgPushSpec push, int discard, int sf_known, int sl_known)
 {
     constexpr int S = G2 + P;
     constexpr int JMAX = SG_POST2_JMAX;
@@ -57,11 +57,12 @@ __global__ void __launch_bounds__(128, 4) sg_adj_post2_kernel(T *__restrict__ cp
     T w[RMAX];
 #pragma unroll
     for (int r = 0; r < RMAX; ++r) w[r] = sg_ldg(g_w + (int64_t)r * c1 + i1c);
-    const int sf = hdr->span_first[2], sl = hdr->span_last[2];
+    // planned calls pass the slab's first / last span of dimension 3 as arguments (one dependent load chain less per CTA)
+    const int sf = sf_known > 0 ? sf_known : hdr->span_first[2], sl = sf_known > 0 ? sl_known : hdr->span_last[2];
     // This kernel writes EVERY control point (no memset before the pipeline): zeros outside the support of this (slab
     // of the) grid, and zeros everywhere if the prep kernel flagged non-monotone spans (the scatter kernel accumulates).
     const bool write_local = push.world == 0 || push.keep_local != 0;
-    if (!sg_adj_path_active(hdr, path) || i3 < sf - P || i3 > sl) {
+    if ((sf_known <= 0 && !sg_adj_path_active(hdr, path)) || i3 < sf - P || i3 > sl) {   // (a plan has seen monotone spans)
         const int64_t iz = ib * 128 + tid;
         if (iz < c1 && write_local) {
             T *__restrict__ out = cp + iz + c1 * (i2_0 + c2 * ((i3 - 1) + c3 * o));
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(128, 4) sg_adj_post2_kernel(T *__restrict__ cp
     int64_t off0 = 0, off1 = 0;
     int nc = 0;
     {
-        const int G3e = sg_m2_chunk_len(hdr, P, chunks3);
+        const int G3e = max(max(P, 1), (sl - sf + 1 + chunks3 - 1) / chunks3);   // == sg_m2_chunk_len
         const int nch = (sl - sf + 1 + G3e - 1) / G3e;                 // chunks that hold samples
         const int c_lo = i3 >= sf ? (int)((i3 - sf) / G3e) : 0;
         const int c_hi = min((int)((i3 - sf + P) / G3e), nch - 1);

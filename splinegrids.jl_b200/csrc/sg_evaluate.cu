@@ -224,6 +224,8 @@ static int sg_evaluate_adjoint_impl(T *cp, int nin, const int64_t *n_samples, co
     known.fused_ok = plan != nullptr && PL.g.ok && plan->h.m2g_bad == 0;
     known.rows2_max = plan ? plan->h.rows2_max : 0;
     known.uni = plan ? plan->uni : nullptr;
+    known.sf3 = (plan && nin == 3) ? plan->h.span_first[2] : 0;
+    known.sl3 = (plan && nin == 3) ? plan->h.span_last[2] : 0;
     rc = SG_OK;
     do {
         cudaError_t e;

@@ -13,6 +13,7 @@ struct SgAdjKnown {
     bool planned;
     bool fused_ok;     // the column-block tables of the fused double march exist and fit
     int rows2_max;     // largest number of samples in one knot span of dimension 2
+    int sf3, sl3;      // first / last span of dimension 3 that holds samples (0: unknown)
     const void *uni;   // host copy of the weights / span starts of dimension 2 (SgM2Uni<T>, sg_adjoint_march2g.cuh) or nullptr
 };
 size_t sg_m2_uni_bytes(int elem_size);

@@ -672,9 +672,9 @@ static int sg_run_march2(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &s
         const int discard = sg_env_int("SG_ADJ_DISCARD", 1) && (m.n1 * sizeof(T)) % 128 == 0 && reinterpret_cast<uintptr_t>(part) % 128 == 0 &&
                             a.n_cp[0] <= 128;
         switch (P) {
-            case 1: sg_adj_post2_kernel<T, 1, SG_M2_G2><<<pgrid, 128, 0, st>>>(cp, part, a.table[0], a.index[0], ss.g_lo, ss.g_w, hdr, m.n1, a.n_cp[0], m.c2, m.c3, a.degree[0], mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS, ps, discard); break;
-            case 2: sg_adj_post2_kernel<T, 2, SG_M2_G2><<<pgrid, 128, 0, st>>>(cp, part, a.table[0], a.index[0], ss.g_lo, ss.g_w, hdr, m.n1, a.n_cp[0], m.c2, m.c3, a.degree[0], mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS, ps, discard); break;
-            default: sg_adj_post2_kernel<T, 3, SG_M2_G2><<<pgrid, 128, 0, st>>>(cp, part, a.table[0], a.index[0], ss.g_lo, ss.g_w, hdr, m.n1, a.n_cp[0], m.c2, m.c3, a.degree[0], mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS, ps, discard); break;
+            case 1: sg_adj_post2_kernel<T, 1, SG_M2_G2><<<pgrid, 128, 0, st>>>(cp, part, a.table[0], a.index[0], ss.g_lo, ss.g_w, hdr, m.n1, a.n_cp[0], m.c2, m.c3, a.degree[0], mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS, ps, discard, known.sf3, known.sl3); break;
+            case 2: sg_adj_post2_kernel<T, 2, SG_M2_G2><<<pgrid, 128, 0, st>>>(cp, part, a.table[0], a.index[0], ss.g_lo, ss.g_w, hdr, m.n1, a.n_cp[0], m.c2, m.c3, a.degree[0], mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS, ps, discard, known.sf3, known.sl3); break;
+            default: sg_adj_post2_kernel<T, 3, SG_M2_G2><<<pgrid, 128, 0, st>>>(cp, part, a.table[0], a.index[0], ss.g_lo, ss.g_w, hdr, m.n1, a.n_cp[0], m.c2, m.c3, a.degree[0], mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS, ps, discard, known.sf3, known.sl3); break;
         }
         g_sg_launches.fetch_add(1);
         return SG_OK;
