@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(128, 4) sg_eval2d_multi_kernel(const __grid_co
     }
     int64_t col1[WD];
 #pragma unroll
-    for (int q = 0; q < WD; ++q) col1[q] = min((int64_t)min1 + q, c1 - 1);
+    for (int q = 0; q < WD; ++q) col1[q] = min(max((int64_t)min1 + q, (int64_t)0), c1 - 1);
 
     T T1[ND][V1][P + 1] = {};
     int cur = -0x40000000;

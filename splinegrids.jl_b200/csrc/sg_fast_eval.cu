@@ -1,4 +1,5 @@
 // sg_fast_eval.cu -- dispatch of the tiled sm_100a fast paths for evaluate! (kernels: sg_fast_eval.cuh).
+#include <cstdio>
 #include <cstdlib>
 
 #include <algorithm>
@@ -182,13 +183,8 @@ static int sg_eval3d_variant(T *eval, const SgGridArgs<T> &a, const T *cp, cudaS
 }
 
 template <typename T>
-int sg_evaluate_fast(T *eval, const SgGridArgs<T> &a, const T *cp, const T *weights, cudaStream_t st)
+static int sg_evaluate_fast_uniform(T *eval, const SgGridArgs<T> &a, int p, const T *cp, const T *weights, cudaStream_t st)
 {
-    int p;
-    if (!sg_uniform_degree(a.degree, a.nin, p)) return SG_ERR_UNSUPPORTED;
-    if (a.nin != 2 && a.nin != 3) return SG_ERR_UNSUPPORTED;
-    if (p < 1 || p > 3) return SG_ERR_UNSUPPORTED;
-    if (g_sg_policy != 2 && a.n_total < 32768) return SG_ERR_UNSUPPORTED;   // launch-latency regime: generic kernel
     if (a.nin == 3) {
         if (weights) return SG_ERR_UNSUPPORTED;
         switch (p) {
@@ -209,6 +205,53 @@ int sg_evaluate_fast(T *eval, const SgGridArgs<T> &a, const T *cp, const T *weig
         case 2: return sg_eval2d_by_nout<T, 2, false>(eval, a, cp, weights, st);
         default: return sg_eval2d_by_nout<T, 3, false>(eval, a, cp, weights, st);
     }
+}
+
+template <typename T>
+int sg_evaluate_fast(T *eval, const SgGridArgs<T> &a, const T *cp, const T *weights, cudaStream_t st)
+{
+    if (a.nin != 2 && a.nin != 3) return SG_ERR_UNSUPPORTED;
+    if (g_sg_policy != 2 && a.n_total < 32768) return SG_ERR_UNSUPPORTED;   // launch-latency regime: generic kernel
+    int p;
+    if (sg_uniform_degree(a.degree, a.nin, p)) {
+        if (p < 1 || p > 3) return SG_ERR_UNSUPPORTED;
+        return sg_evaluate_fast_uniform<T>(eval, a, p, cp, weights, st);
+    }
+    // Mixed degrees (the README grid has (2, 3, 2)): pad every dimension's table to the largest degree with leading zero
+    // columns and run the uniform-degree march kernel of that degree.  Costs one tiny launch per padded dimension and a
+    // stream-ordered scratch allocation, so only grids past the launch-latency regime take it.
+    int pmax = 0;
+    for (int d = 0; d < a.nin; ++d) pmax = std::max(pmax, a.degree[d]);
+    if (pmax < 1 || pmax > 3 || sg_env_int("SG_EVAL_MIXED", 1) == 0) return SG_ERR_UNSUPPORTED;
+    if (g_sg_policy != 2 && a.n_total < 262144) return SG_ERR_UNSUPPORTED;
+    SgGridArgs<T> a2 = a;
+    size_t off[SG_MAX_DIMS], total = 0;
+    for (int d = 0; d < a.nin; ++d) {
+        off[d] = total;
+        if (a.degree[d] != pmax) total += ((size_t)a.n_samples[d] * (pmax + 1) * sizeof(T) + 255) & ~(size_t)255;
+    }
+    char *scratch = nullptr;
+    SG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&scratch), total, st));
+    a2.n_window = 1;
+    for (int d = 0; d < a.nin; ++d) {
+        if (a.degree[d] != pmax) {
+            T *dst = reinterpret_cast<T *>(scratch + off[d]);
+            sg_pad_table_kernel<T><<<sg_blocks(a.n_samples[d], 128), 128, 0, st>>>(dst, a.table[d], a.n_samples[d], a.degree[d], pmax);
+            g_sg_launches.fetch_add(1);
+            a2.table[d] = dst;
+            a2.degree[d] = pmax;
+        }
+        a2.n_window *= pmax + 1;
+    }
+    int rc = sg_evaluate_fast_uniform<T>(eval, a2, pmax, cp, weights, st);
+    cudaError_t e = cudaFreeAsync(scratch, st);
+    if (rc == SG_OK && e != cudaSuccess) rc = (int)e;
+    if (rc == SG_OK) {
+        static thread_local char name[64];
+        snprintf(name, sizeof(name), "%s_mixed", g_sg_last_variant);
+        g_sg_last_variant = name;
+    }
+    return rc;
 }
 
 // ---- several derivative orders in one launch (2-D, uniform degree 1..3, not rational) ----------------------------

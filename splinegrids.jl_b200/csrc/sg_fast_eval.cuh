@@ -96,11 +96,23 @@ __device__ __noinline__ T sg_eval_point_slow(const SgGridArgs<T> &a, const int64
             b *= sg_ldg(a.table[d] + J[d] + a.n_samples[d] * I[d]);
             off += I[d] * a.cp_stride[d];
         }
-        if (NURBS) { b *= sg_ldg(weights + off); den += b; }
-        acc += b * sg_ldg(cp + off + a.cp_total * o);
+        if (NURBS && b != T(0)) { b *= sg_ldg(weights + off); den += b; }
+        if (b != T(0)) acc += b * sg_ldg(cp + off + a.cp_total * o);   // (zero weight: padded entry of a degree-padded table, maybe out of range)
         for (int d = 0; d < a.nin; ++d) { if (++I[d] <= a.degree[d]) break; I[d] = 0; }
     }
     return NURBS ? acc / den : acc;
+}
+
+// Degree padding (mixed degrees on the uniform-degree march kernels): dst (n, pmax+1) = src (n, p+1) with pmax - p leading
+// zero columns.  The window of span idx then starts at idx - pmax - 1 for every dimension (it may reach below control index 0,
+// where the weight is zero and the kernels clamp the address).
+template <typename T>
+__global__ void sg_pad_table_kernel(T *__restrict__ dst, const T *__restrict__ src, int64_t n, int p, int pmax)
+{
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int lead = pmax - p;
+    for (int k = 0; k <= pmax; ++k) dst[j + n * k] = k >= lead ? src[j + n * (k - lead)] : T(0);
 }
 
 // Expanded, zero-padded weights of V consecutive samples of one dimension.
@@ -224,14 +236,14 @@ __global__ void __launch_bounds__(32 * TY) sg_eval3d_march_kernel(T *__restrict_
         int64_t col1[WD], row2[WD];
 #pragma unroll
         for (int q = 0; q < WD; ++q) {
-            col1[q] = min((int64_t)min1 + q, c1 - 1);
-            row2[q] = min((int64_t)min2 + q, c2 - 1) * c1;
+            col1[q] = min(max((int64_t)min1 + q, (int64_t)0), c1 - 1);      // (below 0 only for degree-padded tables: zero weight)
+            row2[q] = min(max((int64_t)min2 + q, (int64_t)0), c2 - 1) * c1;
         }
         T T2[V1][V2][P + 1] = {};
         int cur = -0x40000000;
 
         auto contract_plane = [&](int64_t i3, T (&out)[V1][V2]) {
-            const T *__restrict__ pl = cpo + i3 * c1 * c2;
+            const T *__restrict__ pl = cpo + max(i3, (int64_t)0) * c1 * c2;
             const int p3 = (int)i3 - o3;
             const bool from_tile = TMA && fits12 && p3 >= 0 && p3 < SG_TMA_B3;
             const T *__restrict__ tp = tbase + SG_TMA_B1 * SG_TMA_B2 * (from_tile ? p3 : 0);
@@ -359,12 +371,13 @@ __global__ void __launch_bounds__(128) sg_eval2d_march_kernel(T *__restrict__ ev
     }
     int64_t col1[WD];
 #pragma unroll
-    for (int q = 0; q < WD; ++q) col1[q] = min((int64_t)min1 + q, c1 - 1);
+    for (int q = 0; q < WD; ++q) col1[q] = min(max((int64_t)min1 + q, (int64_t)0), c1 - 1);
 
     T T1[V1][P + 1][NCH] = {};
     int cur = -0x40000000;
 
     auto contract_row = [&](int64_t i2, T (&out)[V1][NCH]) {
+        i2 = max(i2, (int64_t)0);                                      // (degree-padded tables: zero weight)
 #pragma unroll
         for (int v1 = 0; v1 < V1; ++v1)
 #pragma unroll

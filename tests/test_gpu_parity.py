@@ -410,6 +410,34 @@ def test_evaluate_multi_vs_separate_oracle_calls(S, case):
         S.evaluate_multi_(grid, [tuple(mdo + 1 for _ in n_cp)], evs[:1])
 
 
+MIXED_CASES = [
+    ((10, 10, 5), (2, 3, 2), (96, 80, 64), 4, "Float64", 1, False),          # the README degrees on a mid-size grid
+    ((9, 12, 8), (3, 1, 2), (100, 70, 50), 2, "Float32", 1, False),
+    ((14, 9), (1, 3), (700, 500), 3, "Float32", 1, False),
+    ((14, 9), (3, 2), (640, 480), 2, "Float64", 0, True),                     # rational, mixed degrees
+    ((6, 20, 7), (0, 3, 2), (64, 90, 60), 1, "Float64", 0, False),           # a degree-0 dimension
+]
+
+
+@pytest.mark.parametrize("case", MIXED_CASES, ids=[f"{c[0]}-{c[1]}-{c[4]}{'-nurbs' if c[6] else ''}" for c in MIXED_CASES])
+def test_mixed_degree_forward_uses_padded_fast_path(S, case):
+    """Mixed degrees: the tables are padded to the largest degree on the device and the uniform-degree march kernel runs
+    (variant "..._mixed"); against the C oracle for the value and the first derivatives."""
+    from gpu_helpers import make_grid, oracle_evaluate
+    n_cp, deg, n_s, nout, ft, mdo, nurbs = case
+    grid, cp, w, rng = make_grid(n_cp, deg, n_s, nout, ft, mdo=mdo, nurbs=nurbs, seed=67)
+    ders = [(0,) * len(n_cp)]
+    if mdo and not nurbs:
+        ders += [tuple(min(mdo, p) if d == k else 0 for d, p in enumerate(deg)) for k in range(len(n_cp))]
+    for der in ders:
+        grid.eval.fill_(float("nan"))
+        S.evaluate_(grid, derivative_order=der)
+        assert S.last_variant().endswith("_mixed"), S.last_variant()
+        ref = oracle_evaluate(grid, cp, der, w)
+        assert rel_err(S.to_numpy(grid.eval), ref) <= _tol(ft), der
+        assert max_rel_err(S.to_numpy(grid.eval), ref) <= 10 * _tol(ft), der
+
+
 def test_evaluate_with_raw_and_reshaped_arrays(S):
     """control_points / eval kwargs accept raw arrays and reshaped flat vectors (test/test_EnzymeExt.jl:24-28,
     ext/SplineGridsLinearMapsExt.jl:26-30)."""
