@@ -527,7 +527,6 @@ static bool sg_m2_make_eval_maps(SgM2Maps &maps, const T *eval, int64_t n1, int6
 template <typename T, int P>
 static int sg_launch_march2(const SgAdj2Args<T> &m, int nout, const SgAdjKnown &known, cudaStream_t st)
 {
-    const SgM2Uni<T> *uni = static_cast<const SgM2Uni<T> *>(known.uni);
     dim3 grid((unsigned)((m.n1 + 127) / 128), (unsigned)m.tiles2, (unsigned)(m.chunks3 * nout));
     // TMA-fed ring: bulk copies need 16-byte aligned rows; rows per tile are data dependent, so the expected count must
     // fit the ring (tiles that do not are skipped by the TMA kernel and done by the register kernel right after)
@@ -541,15 +540,7 @@ static int sg_launch_march2(const SgAdj2Args<T> &m, int nout, const SgAdjKnown &
         if (g_sg_prof_on) cudaEventRecord(g_sg_prof_ev[0], st);
         SgM2Maps maps{};
         const int use_maps = sg_env_int("SG_ADJ_M2_MAPS", 1) && sg_m2_make_eval_maps<T>(maps, m.X, m.n1, m.n2, m.n3 * nout) ? 1 : 0;
-        if (use_maps && uni != nullptr && known.planned && known.rows2_max <= SG_M2_FAST_ROWS && sg_env_int("SG_ADJ_M2_UNI", 0)) {
-            // opt-in experiment (planned calls): weights of dimension 2 and the span bookkeeping through the uniform datapath
-            // (kernel parameter -> LDCU -> DFMA with uniform operands).  Measured SLOWER than the shared-memory weights
-            // (C3 adjoint 0.242 vs 0.234 ms): the LDCU latency is exposed with three consumer warps per scheduler.
-            auto ku = sg_adj_march2_tma_kernel<T, P, SG_M2_G2, SG_M2_RTMAX, SG_M2_NS, true>;
-            SG_CUDA(cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ku<<<grid, 160, smem, st>>>(m, maps, use_maps, *uni);
-        } else
-            kern<<<grid, 160, smem, st>>>(m, maps, use_maps, SgM2UniNone<T>{});   // 4 consumer warps + 1 producer warp
+        kern<<<grid, 160, smem, st>>>(m, maps, use_maps);                   // 4 consumer warps + 1 producer warp
         if (g_sg_prof_on) { cudaEventRecord(g_sg_prof_ev[1], st); g_sg_prof_recorded = 1; }
         // tiles with more rows than the ring holds (normally none: one idle launch; a plan knows and skips it)
         if (known.planned && known.rows2_max <= SG_M2_FAST_ROWS) {

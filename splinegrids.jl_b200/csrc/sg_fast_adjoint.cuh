@@ -877,10 +877,9 @@ struct SgM2UniNone {};
 // empty[st] : consumers -> producer, 128 arrivals once every consumer has read the stage
 // No block-wide barrier inside the plane loop; the (CTA-uniform) dimension-3 table rows are staged per piece of
 // MAXPL planes.
-template <typename T, int P, int G2, int RTMAX, int NS, bool UW = false>
+template <typename T, int P, int G2, int RTMAX, int NS>
 __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_constant__ SgAdj2Args<T> a, const __grid_constant__ SgM2Maps maps,
-                                                                   int use_maps,
-                                                                   const __grid_constant__ typename std::conditional<UW, SgM2Uni<T>, SgM2UniNone<T>>::type uni)
+                                                                   int use_maps)
 {
     if (!sg_adj_path_active(a.hdr, a.path)) return;
     constexpr int S = G2 + P;
@@ -894,7 +893,7 @@ __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_
     __shared__ int s3s[MAXPL];
     __shared__ int row0[G2 + 1];
     constexpr int RS5 = SG_M2_FAST_ROWS;                                // row slots per span of the straight-line contraction
-    __shared__ __align__(16) T b2pad[UW ? 1 : G2 * RS5 * (P + 1)];      // [span g][row q][k], zero for absent rows
+    __shared__ __align__(16) T b2pad[G2 * RS5 * (P + 1)];               // [span g][row q][k], zero for absent rows
     __shared__ __align__(8) uint64_t full[NS];
     __shared__ __align__(8) uint64_t empty[NS];
 
@@ -910,23 +909,16 @@ __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_
     const int ncols = (int)min((int64_t)CW, a.n1 - j1_0);
 
     const int s2_lo = P + 1 + tile2 * G2;
-    // rows of the tile's spans: [ur0[g], ur0[g + 1]).  UW: from the kernel parameter (uniform registers), else from memory.
+    // rows of the tile's spans: [ur0[g], ur0[g + 1]) (register copies of row0[])
     int ur0[G2 + 1];
-    if constexpr (UW) {
-#pragma unroll
-        for (int g = 0; g <= G2; ++g) ur0[g] = uni.start2[min(s2_lo + g, (int)a.c2 + 1)];
-    } else {
-        if (tid <= G2) row0[tid] = a.start2[(int)min((int64_t)s2_lo + tid, a.c2 + 1)];
-    }
+    if (tid <= G2) row0[tid] = a.start2[(int)min((int64_t)s2_lo + tid, a.c2 + 1)];
     if (tid == 0) {
 #pragma unroll
         for (int q = 0; q < NS; ++q) { sg_mbar_init(&full[q], 1); sg_mbar_init(&empty[q], CW / 32); }   // one arrival per consumer warp
     }
     __syncthreads();
-    if constexpr (!UW) {
 #pragma unroll
-        for (int g = 0; g <= G2; ++g) ur0[g] = row0[g];
-    }
+    for (int g = 0; g <= G2; ++g) ur0[g] = row0[g];
     const int r_first = ur0[0], n_rows = ur0[G2] - ur0[0];
     // Straight-line contraction of dimension 2 (no data-dependent loops, no predicates): a ring stage holds G2 x RS5
     // fixed row slots, slot (g, q) = q-th row of span g of the tile.  The producer copies every present row into its
@@ -940,7 +932,7 @@ __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_
         if (tid == 0) a.hdr->m2_skipped = 1;
         return;
     }
-    if (!UW && !is_producer) {
+    if (!is_producer) {
         for (int q = tid; q < G2 * RS5 * (P + 1); q += CW) {
             const int k = q % (P + 1), gq = q / (P + 1), g = gq / RS5, qq = gq % RS5;
             b2pad[q] = qq < row0[g + 1] - row0[g] ? sg_ldg(a.table2 + (row0[g] + qq) + a.n2 * k) : T(0);
@@ -951,16 +943,12 @@ __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_
         }
     }
 
-    int sf3, sl3;
-    if constexpr (UW) { sf3 = uni.span_first3; sl3 = uni.span_last3; }
-    else { sf3 = a.hdr->span_first[2]; sl3 = a.hdr->span_last[2]; }
+    const int sf3 = a.hdr->span_first[2], sl3 = a.hdr->span_last[2];
     const int G3e = max(max(P, 1), (sl3 - sf3 + 1 + a.chunks3 - 1) / a.chunks3);   // == sg_m2_chunk_len
     const int s3_lo = sf3 + c3k * G3e;
     const int s3_hi = min(s3_lo + G3e, sl3 + 1);
     if (s3_lo >= s3_hi) return;                                        // block-uniform
-    int64_t j3_lo, j3_hi;
-    if constexpr (UW) { j3_lo = uni.start3[s3_lo]; j3_hi = uni.start3[s3_hi]; }
-    else { j3_lo = a.start3[s3_lo]; j3_hi = a.start3[s3_hi]; }
+    const int64_t j3_lo = a.start3[s3_lo], j3_hi = a.start3[s3_hi];
     const int np_total = (int)(j3_hi - j3_lo);
     const int rows3 = a.G3 + P;
 
@@ -1061,17 +1049,9 @@ __global__ void __launch_bounds__(160, 3) sg_adj_march2_tma_kernel(const __grid_
                 for (int g = 0; g < G2; ++g) {
 #pragma unroll
                     for (int q = 0; q < RS5; ++q) {
-                        if constexpr (UW) {
-                            if (q < ur0[g + 1] - ur0[g]) {              // uniform predicate: absent slots cost nothing
-                                const T x = xst[(g * RS5 + q) * CW];
+                        const T x = xst[(g * RS5 + q) * CW];
 #pragma unroll
-                                for (int k = 0; k <= P; ++k) T2[g + k] = fma(uni.b2[(ur0[g] + q) * (P + 1) + k], x, T2[g + k]);
-                            }
-                        } else {
-                            const T x = xst[(g * RS5 + q) * CW];
-#pragma unroll
-                            for (int k = 0; k <= P; ++k) T2[g + k] = fma(b2pad[(g * RS5 + q) * (P + 1) + k], x, T2[g + k]);
-                        }
+                        for (int k = 0; k <= P; ++k) T2[g + k] = fma(b2pad[(g * RS5 + q) * (P + 1) + k], x, T2[g + k]);
                     }
                 }
                 __syncwarp();

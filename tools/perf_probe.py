@@ -19,6 +19,7 @@ CONFIGS = {
     "C3s": dict(n_cp=(128, 128, 128), deg=(3, 3, 3), n_s=(512, 512, 64), nout=1, ft="Float64"),
     "C4": dict(n_cp=(256, 256), deg=(3, 3), n_s=(8192, 8192), nout=3, ft="Float32", nurbs=True),
     "C5s": dict(n_cp=(250, 250), deg=(2, 2), n_s=(4096, 4096), nout=3, ft="Float32"),
+    "C2p": dict(n_cp=(64, 64), deg=(3, 3), n_s=(4160, 4096), nout=3, ft="Float32", mdo=1),    # C2 with a row stride that is not a power of two
     "C5d": dict(n_cp=(18, 18), deg=(2, 2), n_s=(500, 500), nout=3, ft="Float32", mdo=1),      # docs-size finest level of C5
     "M1k": dict(n_cp=(64, 64), deg=(3, 3), n_s=(1024, 1024), nout=3, ft="Float32", mdo=1),
 }
