@@ -21,6 +21,14 @@ def S():
     return sg()
 
 
+@pytest.fixture(autouse=True)
+def _restore_switches(S):
+    """Process-wide test hooks (kernel policy, adjoint plans) go back to their defaults after every test."""
+    yield
+    S.set_adjoint_plans(True)
+    S.set_kernel_policy(0)
+
+
 def _tol(ft):
     return 1e-5 if ft == "Float32" else 1e-12
 
@@ -608,9 +616,10 @@ def test_flag_synchronised_exchange_single_device(S, fused_signal):
 
 @pytest.mark.parametrize("shape", [((12, 9, 40), (2, 3, 3), (128, 40, 96), "adjoint_march2"),
                                    ((9, 8, 40), (3, 2, 3), (40, 36, 96), "adjoint_passes")], ids=["fused", "fallback"])
+@pytest.mark.parametrize("plans", [True, False], ids=["planned", "plain"])
 @pytest.mark.parametrize("world", [2, 3])
-def test_fused_gradient_push_single_device(S, world, shape):
-    """sg_evaluate_adjoint_push with every "rank" simulated on one device (peer pointers = local buffers): after all
+def test_fused_gradient_push_single_device(S, world, shape, plans):
+    """sg_evaluate_adjoint_planned with peer pointers / sg_evaluate_adjoint_push with every "rank" simulated on one device (peer pointers = local buffers): after all
     ranks' calls, every staging buffer holds exactly what adjoint + sg_exchange_push writes, and the reduce gives the
     full-grid gradient.  "fused": the double march's post kernel does the peer stores itself; "fallback": another
     pipeline runs, followed by the separate push kernel inside the same C call."""
@@ -620,6 +629,7 @@ def test_fused_gradient_push_single_device(S, world, shape):
     rng = np.random.default_rng(14)
     n_cp, deg, n_s, variant = shape
     nout = 2
+    S.set_adjoint_plans(plans)
     gdims = tuple(S.SplineDimension(c, p, n, float_type="Float64") for c, p, n in zip(n_cp, deg, n_s))
     full = S.SplineGrid(gdims, nout)
     e = np.asfortranarray(rng.random(n_s + (nout,)))
