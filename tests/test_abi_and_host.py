@@ -112,3 +112,43 @@ def test_slab_bounds_partition(S):
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 1
     assert S.slab_bounds(512, 8, 3) == (192, 256)
+
+
+def test_bench_reference_arm_contract_line():
+    """`bench.py --impl reference` (the CPU arm: the oracle on the host cores) prints ONE JSON line with the contract keys,
+    for the default workload and for another BASELINE config; all host threads are used whatever OMP_NUM_THREADS says."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    env = dict(os.environ, OMP_NUM_THREADS="1")            # what torchrun exports to its workers
+    for extra in ([], ["--config", "C2"]):
+        out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                              "--cpu-planes", "2", *extra], capture_output=True, text=True, env=env, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+        assert len(lines) == 1
+        d = json.loads(lines[0])
+        for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                    "dtype", "data", "config", "cpu_baseline", "e2e"):
+            assert key in d, key
+        assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
+        assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+        assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_oracle_range_activation_row_order_matches_the_reference():
+    """activate_local_control_point_range! flattens the ADJOINT of the Iterators.product array (src/control_points.jl:535-537):
+    for Nin = 2 the rows come out with dimension 2 fastest."""
+    import numpy as np
+    from oracle import oracle_np as O
+    seen = {}
+    O_activate = O.activate_local_refinement
+    try:
+        O.activate_local_refinement = lambda lrcp, idx, *a, **k: seen.setdefault("idx", np.array(idx))
+        O.activate_local_control_point_range(None, (2, 3), (5, 7))
+    finally:
+        O.activate_local_refinement = O_activate
+    assert seen["idx"].tolist() == [[2, 5], [2, 6], [2, 7], [3, 5], [3, 6], [3, 7]]
