@@ -23,6 +23,13 @@ stream_ptr() = Base.unsafe_convert(Ptr{Cvoid}, CUDA.stream().handle)
 devptr(a::CuArray) = reinterpret(Ptr{Cvoid}, pointer(a))
 devptr(::Nothing) = C_NULL
 
+int32_device(a::CuArray{Int32}) = a
+int32_device(a::CuArray{<:Integer}) = Int32.(a)            # a NEW device array: the caller keeps it rooted
+
+mutable struct AdjointPlan
+    handle::Ptr{Cvoid}
+end
+
 # The symbol must be a constant for ccall: generate one method per float type.
 for (Tv, suf) in ((Float32, "f32"), (Float64, "f64"))
     sym(name) = QuoteNode(Symbol(name, "_", suf))
@@ -210,12 +217,6 @@ for (Tv, suf) in ((Float32, "f32"), (Float64, "f64"))
     end
 end
 
-int32_device(a::CuArray{Int32}) = a
-int32_device(a::CuArray{<:Integer}) = Int32.(a)            # a NEW device array: the caller keeps it rooted
-
-mutable struct AdjointPlan
-    handle::Ptr{Cvoid}
-end
 
 # ---- hierarchy loops with the two kernel launches replaced (the loops themselves are the reference's) -------------------
 function SplineGrids.evaluate!(control_points::LocallyRefinedControlPoints{Nin, Nout, Tv, Int32, <:CuArray}) where {Nin, Nout, Tv}
