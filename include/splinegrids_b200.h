@@ -371,6 +371,33 @@ int sg_exchange_wait_reduce_f64(double *grad, const double *stage, const void *m
                                 void *const *peer_flags_or_null, int world, int my_rank, const int64_t *k0s, const int64_t *nps,
                                 int64_t plane_elems, int64_t c_last, int nout, int64_t max_planes, void *stream);
 
+/* ---- support-plane exchange: the halo variant of the two calls above (new; the reference is single-device) -----------
+ * evaluate! on a slab reads only the control planes of the slab's support [k0s[r], k0s[r] + nps[r]) (0-based planes of the
+ * slowest control axis), so a fitting loop evaluate! -> evaluate_adjoint! -> update needs the SUMMED gradient on those planes
+ * only.  sg_evaluate_adjoint_planned_support pushes every finished plane to the ranks whose support contains it (the p halo
+ * planes a slab shares with each neighbour) instead of to all ranks; sg_exchange_wait_reduce_support signals and waits for
+ * those neighbours only -- no global barrier -- and writes grad[:, k, :] for the planes k of its own support (summed in rank
+ * order: bit-identical on every rank that holds the plane and to sg_exchange_wait_reduce); all other planes of `grad` are left
+ * untouched.  Per-rank NVLink ingress drops from (world - 1)/world of the gradient to the halo planes.  Same staging layout,
+ * flags, local_sync and two-buffer rule as above; every rank must use the same variant in a given exchange.  k0s / nps: HOST
+ * arrays of `world` entries.  Pipelines without the fused push fall back to a push of all planes to all ranks (correct). */
+int sg_evaluate_adjoint_planned_support_f32(const sg_adjoint_plan *plan, float *cp, const float *eval, const float *weights_or_null,
+                                            void *workspace, size_t workspace_bytes, void *const *peer_stage, int world,
+                                            int my_rank, const int64_t *k0s, const int64_t *nps, int64_t max_planes,
+                                            int keep_local, void *stream);
+int sg_evaluate_adjoint_planned_support_f64(const sg_adjoint_plan *plan, double *cp, const double *eval, const double *weights_or_null,
+                                            void *workspace, size_t workspace_bytes, void *const *peer_stage, int world,
+                                            int my_rank, const int64_t *k0s, const int64_t *nps, int64_t max_planes,
+                                            int keep_local, void *stream);
+int sg_exchange_wait_reduce_support_f32(float *grad, const float *stage, const void *my_flags, void *local_sync,
+                                        void *const *peer_flags_or_null, int world, int my_rank, const int64_t *k0s,
+                                        const int64_t *nps, int64_t plane_elems, int64_t c_last, int nout, int64_t max_planes,
+                                        void *stream);
+int sg_exchange_wait_reduce_support_f64(double *grad, const double *stage, const void *my_flags, void *local_sync,
+                                        void *const *peer_flags_or_null, int world, int my_rank, const int64_t *k0s,
+                                        const int64_t *nps, int64_t plane_elems, int64_t c_last, int nout, int64_t max_planes,
+                                        void *stream);
+
 #ifdef __cplusplus
 }
 #endif

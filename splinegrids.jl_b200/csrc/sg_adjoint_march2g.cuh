@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(128) sg_adj_combine2g_kernel(T *__restrict__ c
             const int64_t off = push.max_planes * plane_elems * (o + (int64_t)gridDim.z * push.my_rank) + plane_elems * l + i1 + c1 * i2_0;
 #pragma unroll 1
             for (int r = 0; r < push.n_dst; ++r) {
+                if (l < push.dst_lo[r] || l >= push.dst_hi[r]) continue;
                 T *__restrict__ stg = static_cast<T *>(push.stage[r]) + off;
 #pragma unroll
                 for (int q = 0; q < G2; ++q)

@@ -110,6 +110,9 @@ struct SgPushSpec {
     int n_dst;                   // destinations the kernel stores to: `world` peer pointers, or 1 = stage[0] is a MULTICAST address
                                  // (NVLS: one store, the NVSwitch replicates it into every rank's buffer -- 1/world of the egress)
     long long max_planes;
+    int dst_lo[SG_MAX_PEERS];    // destination r receives the LOCAL planes [dst_lo[r], dst_hi[r]) of this rank's support: everything
+    int dst_hi[SG_MAX_PEERS];    // (0, max_planes) in the replicated exchange; only the planes rank r's own slab touches in the
+                                 // support-plane exchange (sg_evaluate_adjoint_planned_support_*)
     int keep_local;              // 0: the caller does not need the local partial gradient (the reduce overwrites it): the fused
                                  // pipeline then skips its own writes of the control-point array (zeros and results)
 };

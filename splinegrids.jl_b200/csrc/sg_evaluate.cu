@@ -352,7 +352,8 @@ static int sg_adjoint_push_impl(const sg_adjoint_plan *plan, T *cp, int nin, con
                                 const T *const *tables, const int32_t *const *indices, const int *degree, const int *mdo,
                                 const int *der, const T *eval, const T *weights, void *workspace, size_t workspace_bytes,
                                 void *const *peer_stage, int world, int my_rank, int64_t k0, int64_t np, int64_t max_planes,
-                                int keep_local, void *stream, PushFn push_fn, void *multicast_stage = nullptr)
+                                int keep_local, void *stream, PushFn push_fn, void *multicast_stage = nullptr,
+                                const int64_t *k0s = nullptr, const int64_t *nps = nullptr)
 {
     if (!peer_stage || world < 1 || world > SG_MAX_PEERS || my_rank < 0 || my_rank >= world || nin < 1)
         return SG_ERR_INVALID_ARGUMENT;
@@ -360,7 +361,18 @@ static int sg_adjoint_push_impl(const sg_adjoint_plan *plan, T *cp, int nin, con
     for (int r = 0; r < world; ++r) spec.stage[r] = peer_stage[r];
     spec.world = world; spec.my_rank = my_rank; spec.max_planes = max_planes; spec.keep_local = keep_local;
     spec.n_dst = world;
-    if (multicast_stage != nullptr) { spec.stage[0] = multicast_stage; spec.n_dst = 1; }   // one store reaches every rank
+    for (int r = 0; r < SG_MAX_PEERS; ++r) { spec.dst_lo[r] = 0; spec.dst_hi[r] = (int)std::min<int64_t>(max_planes, INT32_MAX); }
+    if (k0s && nps) {
+        // support-plane exchange: rank r only needs the planes its own slab touches, i.e. the overlap of the two supports
+        // (ranks whose supports do not meet receive nothing); the own slot always gets every plane
+        for (int r = 0; r < world; ++r) {
+            if (r == my_rank) continue;
+            const int64_t lo = std::max(k0s[r], k0s[my_rank]) - k0s[my_rank];
+            const int64_t hi = std::min(k0s[r] + nps[r], k0s[my_rank] + nps[my_rank]) - k0s[my_rank];
+            spec.dst_lo[r] = (int)std::max<int64_t>(lo, 0);
+            spec.dst_hi[r] = (int)std::max<int64_t>(std::min<int64_t>(hi, max_planes), spec.dst_lo[r]);
+        }
+    } else if (multicast_stage != nullptr) { spec.stage[0] = multicast_stage; spec.n_dst = 1; }   // one store reaches every rank
     g_sg_push = &spec; g_sg_push_done = false;
     int rc = sg_evaluate_adjoint_impl<T>(cp, nin, n_samples, n_cp, nout, tables, indices, degree, mdo, der, eval, weights,
                                          workspace, workspace_bytes, stream, plan);
@@ -435,6 +447,22 @@ static int sg_adjoint_push_impl(const sg_adjoint_plan *plan, T *cp, int nin, con
                                        plan->indices, plan->degree, plan->mdo, plan->der, eval, weights, workspace,  \
                                        workspace_bytes, peer_stage, world, my_rank, k0, np, max_planes, keep_local,  \
                                        stream, sg_exchange_push_##SUF, multicast_stage);                             \
+    }                                                                                                                \
+    extern "C" int sg_evaluate_adjoint_planned_support_##SUF(const sg_adjoint_plan *plan, T *cp, const T *eval,      \
+                                                     const T *weights, void *workspace, size_t workspace_bytes,      \
+                                                     void *const *peer_stage, int world, int my_rank,                \
+                                                     const int64_t *k0s, const int64_t *nps, int64_t max_planes,     \
+                                                     int keep_local, void *stream)                                   \
+    {                                                                                                                \
+        if (!plan || plan->elem_size != (int)sizeof(T) || (plan->rational != (weights != nullptr)) || !peer_stage || \
+            !k0s || !nps || world < 1 || my_rank < 0 || my_rank >= world)                                            \
+            return SG_ERR_INVALID_ARGUMENT;                                                                          \
+        const T *tb[SG_MAX_DIMS];                                                                                    \
+        for (int d = 0; d < plan->nin; ++d) tb[d] = static_cast<const T *>(plan->tables[d]);                         \
+        return sg_adjoint_push_impl<T>(plan, cp, plan->nin, plan->n_samples, plan->n_cp, plan->nout, tb,             \
+                                       plan->indices, plan->degree, plan->mdo, plan->der, eval, weights, workspace,  \
+                                       workspace_bytes, peer_stage, world, my_rank, k0s[my_rank], nps[my_rank],      \
+                                       max_planes, keep_local, stream, sg_exchange_push_##SUF, nullptr, k0s, nps);   \
     }
 
 SG_DEFINE_EVAL_API(float, f32)

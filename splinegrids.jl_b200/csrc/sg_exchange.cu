@@ -160,9 +160,10 @@ __device__ __forceinline__ unsigned long long sg_globaltimer()
 }
 
 // thread r < world of ONE block: tell rank r that this rank's push number `e` has landed
-__device__ __forceinline__ void sg_exchange_signal_peers(const SgFlagPtrs &pf, int world, int my_rank, unsigned long long e)
+__device__ __forceinline__ void sg_exchange_signal_peers(const SgFlagPtrs &pf, int world, int my_rank, unsigned long long e,
+                                                         unsigned peer_mask = 0xffffffffu)
 {
-    if ((int)threadIdx.x < world) {
+    if ((int)threadIdx.x < world && ((peer_mask >> threadIdx.x) & 1u)) {
         __threadfence_system();                                      // the pushes of the preceding kernels, cumulatively
         sg_st_release_sys(pf.flags[threadIdx.x] + my_rank, e);
     }
@@ -174,9 +175,10 @@ __global__ void sg_exchange_signal_kernel(const __grid_constant__ SgFlagPtrs pf,
 }
 
 // thread r < world of every block waits for flags[r] >= e; returns after a block barrier (all threads may read the stage)
-__device__ __forceinline__ void sg_exchange_wait_all(const unsigned long long *my_flags, int world, unsigned long long e, SgExchangeSync *sync)
+__device__ __forceinline__ void sg_exchange_wait_all(const unsigned long long *my_flags, int world, unsigned long long e, SgExchangeSync *sync,
+                                                     unsigned peer_mask = 0xffffffffu)
 {
-    if ((int)threadIdx.x < world) {
+    if ((int)threadIdx.x < world && ((peer_mask >> threadIdx.x) & 1u)) {
         const unsigned long long t0 = sg_globaltimer();
         while (sg_ld_acquire_sys(my_flags + threadIdx.x) < e) {
             __nanosleep(64);
@@ -192,13 +194,16 @@ template <typename T, int V>
 __global__ void __launch_bounds__(256) sg_exchange_wait_reduce_kernel(T *__restrict__ grad, const T *stage, const unsigned long long *my_flags,
                                                                       SgExchangeSync *sync, const __grid_constant__ SgFlagPtrs pf, int do_signal,
                                                                       int my_rank, const __grid_constant__ SgSupports sup, int world,
-                                                                      int64_t plane_elems, int64_t c_last, int nout, int64_t max_planes)
+                                                                      int64_t plane_elems, int64_t c_last, int nout, int64_t max_planes,
+                                                                      unsigned peer_mask, int64_t k_first)
 {
+    // peer_mask / k_first: the support-plane exchange signals and waits for the ranks whose supports meet this rank's only,
+    // and reduces planes k_first .. k_first + gridDim.y - 1 (this rank's support); the replicated exchange passes ~0 / 0
     const unsigned long long e = sync->epoch + 1;                    // nobody writes epoch while blocks of this launch can still read it
-    if (do_signal && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) sg_exchange_signal_peers(pf, world, my_rank, e);
-    sg_exchange_wait_all(my_flags, world, e, sync);
+    if (do_signal && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) sg_exchange_signal_peers(pf, world, my_rank, e, peer_mask);
+    sg_exchange_wait_all(my_flags, world, e, sync, peer_mask);
 
-    const int64_t k = blockIdx.y;
+    const int64_t k = k_first + blockIdx.y;
     const int o = blockIdx.z;
     T *__restrict__ dst = grad + plane_elems * (k + c_last * o);
     const int64_t n_vec = plane_elems / V;
@@ -283,7 +288,7 @@ extern "C" int sg_exchange_status(const void *local_sync, unsigned long long *ep
 template <typename T>
 static int sg_exchange_wait_reduce_impl(T *grad, const T *stage, const void *my_flags, void *local_sync, void *const *peer_flags_or_null,
                                         int world, int my_rank, const int64_t *k0s, const int64_t *nps, int64_t plane_elems,
-                                        int64_t c_last, int nout, int64_t max_planes, void *stream)
+                                        int64_t c_last, int nout, int64_t max_planes, void *stream, bool support_only = false)
 {
     SG_NVTX("sg_exchange_wait_reduce");
     SG_CHECK_ARG(grad && stage && my_flags && local_sync && k0s && nps && world >= 1 && plane_elems >= 1 && c_last >= 1 && nout >= 1);
@@ -301,13 +306,22 @@ static int sg_exchange_wait_reduce_impl(T *grad, const T *stage, const void *my_
     // ~4 vectors per thread; the whole grid is resident at once for the usual sizes (the spin needs no particular order:
     // a block only waits for PEERS, and every peer's signal is issued by the first block of its own launch)
     const int64_t nv = plane_elems / (vec ? VV : 1);
-    dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((nv + 1023) / 1024, 16)), (unsigned)c_last, (unsigned)nout);
+    unsigned mask = 0xffffffffu;
+    int64_t k_first = 0, n_planes = c_last;
+    if (support_only) {                                              // ranks whose supports overlap this rank's (and this rank)
+        SG_CHECK_ARG(k0s[my_rank] >= 0 && nps[my_rank] >= 1 && k0s[my_rank] + nps[my_rank] <= c_last);
+        mask = 0;
+        for (int r = 0; r < world; ++r)
+            if (r == my_rank || (k0s[r] < k0s[my_rank] + nps[my_rank] && k0s[my_rank] < k0s[r] + nps[r])) mask |= 1u << r;
+        k_first = k0s[my_rank]; n_planes = nps[my_rank];
+    }
+    dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((nv + 1023) / 1024, 16)), (unsigned)n_planes, (unsigned)nout);
     auto *sy = static_cast<SgExchangeSync *>(local_sync);
     auto *fl = static_cast<const unsigned long long *>(my_flags);
     if (vec)
-        sg_exchange_wait_reduce_kernel<T, VV><<<grid, 256, 0, sg_stream(stream)>>>(grad, stage, fl, sy, pf, peer_flags_or_null ? 1 : 0, my_rank, sup, world, plane_elems, c_last, nout, max_planes);
+        sg_exchange_wait_reduce_kernel<T, VV><<<grid, 256, 0, sg_stream(stream)>>>(grad, stage, fl, sy, pf, peer_flags_or_null ? 1 : 0, my_rank, sup, world, plane_elems, c_last, nout, max_planes, mask, k_first);
     else
-        sg_exchange_wait_reduce_kernel<T, 1><<<grid, 256, 0, sg_stream(stream)>>>(grad, stage, fl, sy, pf, peer_flags_or_null ? 1 : 0, my_rank, sup, world, plane_elems, c_last, nout, max_planes);
+        sg_exchange_wait_reduce_kernel<T, 1><<<grid, 256, 0, sg_stream(stream)>>>(grad, stage, fl, sy, pf, peer_flags_or_null ? 1 : 0, my_rank, sup, world, plane_elems, c_last, nout, max_planes, mask, k_first);
     SG_AFTER_LAUNCH();
     return SG_OK;
 }
@@ -326,6 +340,14 @@ static int sg_exchange_wait_reduce_impl(T *grad, const T *stage, const void *my_
     {                                                                                                                           \
         return sg_exchange_wait_reduce_impl<T>(grad, stage, my_flags, local_sync, peer_flags_or_null, world, my_rank, k0s, nps, \
                                                plane_elems, c_last, nout, max_planes, stream);                                  \
+    }                                                                                                                           \
+    extern "C" int sg_exchange_wait_reduce_support_##SUF(T *grad, const T *stage, const void *my_flags, void *local_sync,       \
+                                                 void *const *peer_flags_or_null, int world, int my_rank, const int64_t *k0s,   \
+                                                 const int64_t *nps, int64_t plane_elems, int64_t c_last, int nout,             \
+                                                 int64_t max_planes, void *stream)                                             \
+    {                                                                                                                           \
+        return sg_exchange_wait_reduce_impl<T>(grad, stage, my_flags, local_sync, peer_flags_or_null, world, my_rank, k0s, nps, \
+                                               plane_elems, c_last, nout, max_planes, stream, true);                            \
     }                                                                                                                           \
     extern "C" int sg_exchange_reduce_##SUF(T *grad, const T *stage, int world, const int64_t *k0s, const int64_t *nps,        \
                                             int64_t plane_elems, int64_t c_last, int nout, int64_t max_planes, void *stream)   \

@@ -68,9 +68,18 @@ class PeerGradientExchange:
     order -> deterministic).  No host-side barrier, no collective call: the whole step is plain kernels and can be
     captured in a CUDA graph.  Buffers are ``torch.distributed._symmetric_memory`` allocations (plumbing: allocation and
     the exchange of the peer pointers only); the kernels and the barrier are ours.  Two staging buffers alternate.
+
+    ``mode="support"`` (the halo variant, ``sg_evaluate_adjoint_planned_support`` / ``sg_exchange_wait_reduce_support``):
+    ``evaluate!`` on a slab reads only the control planes of the slab's support, so a fitting loop needs the summed
+    gradient on THOSE planes only.  Every finished plane then goes to the ranks whose support contains it (the ``p`` halo
+    planes shared with each neighbour), the flag barrier involves those neighbours only, and the reduce writes the planes
+    ``support_planes()`` of the gradient (bit-identical to the replicated exchange there) and leaves the others untouched.
     """
 
-    def __init__(self, global_dims: Sequence[SplineDimension], Nout: int, rank: int, world_size: int, group=None):
+    def __init__(self, global_dims: Sequence[SplineDimension], Nout: int, rank: int, world_size: int, group=None,
+                 mode: str = "replicated"):
+        assert mode in ("replicated", "support")
+        self.mode = mode
         import numpy as np
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
@@ -123,19 +132,23 @@ class PeerGradientExchange:
         from . import _lib
         b = self.step & 1
         self.step += 1
-        push = (b, self.peer_ptrs[b], self.world, self.rank, self.k0[self.rank], self.np_[self.rank], self.max_planes, 0,
-                self.mc_ptrs[b])
+        if self.mode == "support":
+            push = ((b, "support"), self.peer_ptrs[b], self.world, self.rank, self.k0[self.rank], self.np_[self.rank],
+                    self.max_planes, 0, 0, (self._k0s, self._nps))
+        else:
+            push = (b, self.peer_ptrs[b], self.world, self.rank, self.k0[self.rank], self.np_[self.rank], self.max_planes, 0,
+                    self.mc_ptrs[b])
         evaluate_adjoint_(grid, control_points=control_points, _push=push, **kw)
         return self._wait_reduce_(control_points, b, _lib.stream_ptr(self.device))
 
     def _wait_reduce_(self, grad: torch.Tensor, b: int, st) -> torch.Tensor:
         from . import _lib
         C = _lib.C
-        key = ("wait_reduce", b, grad.data_ptr())
+        key = ("wait_reduce", b, grad.data_ptr(), self.mode)
         prep = self._prepared.get(key)
         if prep is None:
             suf = _lib.suffix(self.dtype)
-            prep = (getattr(_lib.lib(), "sg_exchange_wait_reduce_" + suf),
+            prep = (getattr(_lib.lib(), "sg_exchange_wait_reduce_" + ("support_" if self.mode == "support" else "") + suf),
                     (_lib.ptr(grad), _lib.ptr(self.stage[b]), _lib.ptr(self.flags), _lib.ptr(self.sync), self.peer_flags,
                      C.c_int(self.world), C.c_int(self.rank), self._k0s, self._nps, C.c_int64(self.plane_elems),
                      C.c_int64(self.c_last), C.c_int(self.nout), C.c_int64(self.max_planes)))
@@ -144,6 +157,11 @@ class PeerGradientExchange:
             self._prepared[key] = prep
         _lib.check(prep[0](*prep[1], st), "sg_exchange_wait_reduce")
         return grad
+
+    def support_planes(self, rank: Optional[int] = None) -> Tuple[int, int]:
+        """0-based control planes ``[lo, hi)`` of the slowest axis that rank's slab touches (= reads in ``evaluate!``)."""
+        r = self.rank if rank is None else rank
+        return self.k0[r], self.k0[r] + self.np_[r]
 
     def exchange_(self, grad: torch.Tensor) -> torch.Tensor:
         """Push kernel + (signal, wait, reduce) kernel on an already computed local partial gradient."""
@@ -185,7 +203,7 @@ class SlabShardedGrid:
     """
 
     def __init__(self, global_dims: Sequence[SplineDimension], Nout: int, rank: int, world_size: int,
-                 nurbs: bool = False, group=None, peer_exchange: bool = False):
+                 nurbs: bool = False, group=None, peer_exchange: bool = False, exchange_mode: str = "replicated"):
         self.global_dims = tuple(global_dims)
         self.rank, self.world_size, self.group = rank, world_size, group
         self.exchange = None
@@ -198,9 +216,12 @@ class SlabShardedGrid:
         self.local: SplineGrid = NURBSGrid(dims, Nout) if nurbs else SplineGrid(dims, Nout)
         if peer_exchange and world_size > 1:
             try:
-                self.exchange = PeerGradientExchange(self.global_dims, Nout, rank, world_size, group)
+                self.exchange = PeerGradientExchange(self.global_dims, Nout, rank, world_size, group, mode=exchange_mode)
                 self.exchange_kind = ("peer_memory_push + device-side flag barrier + reduce (push fused into the adjoint's last "
                                       "kernel; signal, wait and reduce are one kernel)")
+                if exchange_mode == "support":
+                    self.exchange_kind += ("; support-plane exchange: each rank ends with the summed gradient on the control "
+                                           "planes its slab reads, halo planes go to the neighbouring ranks only")
             except Exception as e:   # symmetric memory unavailable: keep the NCCL all-reduce
                 import warnings
                 warnings.warn(f"peer-memory gradient exchange unavailable ({e!r}); using the NCCL all-reduce")

@@ -271,7 +271,7 @@ def evaluate_adjoint_(obj, *, derivative_order: Optional[Sequence[int]] = None, 
     control_points = grid.control_points if control_points is None else control_points
     eval_ = grid.eval if eval is None else eval
     cp = obtain(control_points)
-    # _push = (tag, peer_ptrs, world, rank, k0, np, max_planes[, keep_local]): fused gradient push (distributed.PeerGradientExchange)
+    # _push = (tag, peer_ptrs, world, rank, k0, np, max_planes[, keep_local, multicast_ptr, (k0s, nps)]): fused gradient push (distributed.PeerGradientExchange)
     key = _prepared_key(("adj", adjoint_plans()) if _push is None else ("adj_push", _push[0], adjoint_plans()), grid, der, cp, eval_)
     prep = grid.__dict__.get("_prepared", {}).get(key)
     if prep is None:
@@ -293,10 +293,17 @@ def evaluate_adjoint_(obj, *, derivative_order: Optional[Sequence[int]] = None, 
         if _push is not None:
             _, peer_ptrs, world, rank, k0, np_, max_planes = _push[:7]
             keep_local = _push[7] if len(_push) > 7 else 1
-            args = args + (peer_ptrs, C.c_int(world), C.c_int(rank), C.c_int64(k0), C.c_int64(np_), C.c_int64(max_planes),
-                           C.c_int(keep_local))
-            if plan is not None:                       # NVLS multicast address of the staging buffers (0: none)
-                args = args + (C.c_void_p(_push[8] if len(_push) > 8 else 0),)
+            supports = _push[9] if len(_push) > 9 else None
+            if plan is not None and supports is not None:
+                # support-plane exchange: planes go to the ranks whose slabs read them only (supports = (k0s, nps) of all ranks)
+                fn = getattr(_lib.lib(), "sg_evaluate_adjoint_planned_support_" + _lib.suffix(grid.dtype))
+                args = args + (peer_ptrs, C.c_int(world), C.c_int(rank), supports[0], supports[1], C.c_int64(max_planes),
+                               C.c_int(keep_local))
+            else:
+                args = args + (peer_ptrs, C.c_int(world), C.c_int(rank), C.c_int64(k0), C.c_int64(np_), C.c_int64(max_planes),
+                               C.c_int(keep_local))
+                if plan is not None:                   # NVLS multicast address of the staging buffers (0: none)
+                    args = args + (C.c_void_p(_push[8] if len(_push) > 8 else 0),)
         prep = (fn, args, grid.device.index, ws, plan)
         _prepared_store(grid, key, prep)
     fn, args, dev_index = prep[0], prep[1], prep[2]

@@ -110,6 +110,25 @@ def _worker(rank: int, world: int, port: int, out_dir: str):
         g0 = mine.clone()
         dist.broadcast(g0, 0)
         assert torch.equal(g0, mine)
+        # ---- support-plane exchange (halo variant): summed gradient on the planes this rank's slab reads -------------
+        full_grad = grad.clone()
+        sh2 = S.SlabShardedGrid(gdims, nout, rank, world, peer_exchange=True, exchange_mode="support")
+        assert sh2.exchange is not None and sh2.exchange.mode == "support"
+        lo, hi = sh2.exchange.support_planes()
+        def step2():
+            sh2.evaluate_adjoint_(eval=e_loc, control_points=grad)
+        cap2 = S.CapturedCalls(step2, unroll=2, warmup=1)
+        for it in range(4):
+            grad.fill_(float("nan"))
+            if it < 2:
+                step2()
+            else:
+                cap2.replay()
+            torch.cuda.synchronize()
+            assert S.last_variant().startswith("adjoint_march2")
+            assert torch.equal(grad[:, :, lo:hi, :], full_grad[:, :, lo:hi, :]), it     # same bits as the replicated exchange
+            assert bool(torch.isnan(grad[:, :, :lo, :]).all()) and bool(torch.isnan(grad[:, :, hi:, :]).all())
+        assert not sh2.exchange.status()[1]
         Path(out_dir, f"ok{rank}").write_text("ok")
     finally:
         dist.destroy_process_group()

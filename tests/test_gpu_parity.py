@@ -676,6 +676,79 @@ def test_fused_gradient_push_single_device(S, world, shape, plans):
         assert rel_err(S.to_numpy(grads[r]), ref_grad) <= 1e-12
 
 
+@pytest.mark.parametrize("shape", [((12, 9, 40), (2, 3, 3), (128, 40, 96), "adjoint_march2"),
+                                   ((9, 8, 40), (3, 2, 3), (40, 36, 96), "adjoint_passes")], ids=["fused", "fallback"])
+@pytest.mark.parametrize("world", [2, 4])
+def test_support_plane_exchange_single_device(S, world, shape):
+    """sg_evaluate_adjoint_planned_support + sg_exchange_wait_reduce_support (the halo variant of the gradient exchange) with
+    every "rank" simulated on one device, one stream per rank: each rank ends with the full-grid gradient on the control
+    planes ITS slab reads, bit-identical to the replicated exchange there; the other planes are not written by the exchange;
+    the fused pipeline stores into a neighbour's staging slot only the planes the two supports share."""
+    import ctypes as C
+    from gpu_helpers import oracle_adjoint
+    lib = S._lib.lib()
+    rng = np.random.default_rng(41)
+    n_cp, deg, n_s, variant = shape
+    nout = 2
+    gdims = tuple(S.SplineDimension(c, p, n, float_type="Float64") for c, p, n in zip(n_cp, deg, n_s))
+    full = S.SplineGrid(gdims, nout)
+    e = np.asfortranarray(rng.random(n_s + (nout,)))
+    ref_grad = oracle_adjoint(full, e)
+    idx3 = S.to_numpy(gdims[2].sample_indices)
+    shards = [S.SlabShardedGrid(gdims, nout, r, world) for r in range(world)]
+    k0 = [int(idx3[sh.lo]) - deg[2] - 1 for sh in shards]
+    npl = [int(idx3[sh.hi - 1]) - k for sh, k in zip(shards, k0)]
+    max_planes, plane = max(npl), n_cp[0] * n_cp[1]
+    slot = world * nout * max_planes * plane
+    k0s, nps = S._lib.i64_array(k0), S._lib.i64_array(npl)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    eins = [S.to_device(e[:, :, sh.lo:sh.hi, :]) for sh in shards]
+
+    def run(support):
+        stages = [torch.full((slot,), float("nan"), dtype=torch.float64, device="cuda") for _ in range(world)]
+        peer = (C.c_void_p * world)(*[t.data_ptr() for t in stages])
+        flags = [torch.zeros(16, dtype=torch.int64, device="cuda") for _ in range(world)]
+        syncs = [torch.zeros(8, dtype=torch.int64, device="cuda") for _ in range(world)]
+        peer_flags = (C.c_void_p * world)(*[t.data_ptr() for t in flags])
+        grads = [torch.full_like(sh.local.control_points.obtain(), 3.0) for sh in shards]
+        torch.cuda.synchronize()
+        for r, sh in enumerate(shards):
+            with torch.cuda.stream(streams[r]):
+                push = (("s", r, support), peer, world, r, k0[r], npl[r], max_planes, 0, 0) + (((k0s, nps),) if support else ())
+                S.evaluate_adjoint_(sh.local, eval=eins[r], control_points=grads[r], _push=push)
+                assert S.last_variant().startswith(variant)
+        for r in range(world):
+            fn = lib.sg_exchange_wait_reduce_support_f64 if support else lib.sg_exchange_wait_reduce_f64
+            S._lib.check(fn(S._lib.ptr(grads[r]), S._lib.ptr(stages[r]), S._lib.ptr(flags[r]), S._lib.ptr(syncs[r]), peer_flags,
+                            C.c_int(world), C.c_int(r), k0s, nps, C.c_int64(plane), C.c_int64(n_cp[2]), C.c_int(nout),
+                            C.c_int64(max_planes), C.c_void_p(streams[r].cuda_stream)), "wait_reduce")
+        torch.cuda.synchronize()
+        for r in range(world):
+            ep, to = C.c_ulonglong(0), C.c_int(0)
+            S._lib.check(lib.sg_exchange_status(S._lib.ptr(syncs[r]), C.byref(ep), C.byref(to), None), "status")
+            assert ep.value == 1 and to.value == 0
+        return stages, grads
+
+    st_rep, g_rep = run(False)
+    st_sup, g_sup = run(True)
+    fused = variant.startswith("adjoint_march2")
+    for r in range(world):
+        lo, hi = k0[r], k0[r] + npl[r]
+        got = S.to_numpy(g_sup[r])
+        assert rel_err(got[:, :, lo:hi, :], ref_grad[:, :, lo:hi, :]) <= 1e-12
+        assert torch.equal(g_sup[r][:, :, lo:hi, :], g_rep[r][:, :, lo:hi, :])          # same bits as the replicated exchange
+        rest = np.concatenate([got[:, :, :lo, :].ravel(), got[:, :, hi:, :].ravel()])
+        assert rest.size > 0 and np.all(rest == (3.0 if fused else 0.0))                # not written by the exchange
+        if fused:
+            st = S.to_numpy(st_sup[r]).reshape((plane, max_planes, nout, world), order="F")
+            for q in range(world):
+                if q == r:
+                    continue
+                shared = [l for l in range(npl[q]) if lo <= k0[q] + l < hi]
+                other = [l for l in range(max_planes) if l not in shared]
+                assert not np.isnan(st[:, shared, :, q]).any() and np.isnan(st[:, other, :, q]).all()
+
+
 def test_nurbs_adjoint_is_transpose_of_forward(S):
     """The NURBS adjoint has no reference behaviour (src/adjoint.jl:52-57): pin it as the exact transpose of our
     own forward map via <R p, e> = <p, R' e>, and as the plain adjoint when all weights are 1."""
