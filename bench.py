@@ -604,7 +604,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nccl-allreduce", action="store_true", help="N>1: use the NCCL all-reduce instead of the peer-memory exchange")
-    ap.add_argument("--exchange", choices=["replicated", "support"], default=os.environ.get("SG_BENCH_EXCHANGE", "replicated"),
+    ap.add_argument("--exchange", choices=["replicated", "support"], default=os.environ.get("SG_BENCH_EXCHANGE", "support"),
                     help="N>1 gradient exchange: 'replicated' = every rank ends with the whole summed gradient; 'support' = every "
                          "rank ends with the summed gradient on the control planes its slab reads (halo exchange with the "
                          "neighbouring ranks only)")

@@ -264,6 +264,33 @@ function exchange_wait_reduce!(grad::CuArray{Float64}, my_stage::CuArray{Float64
               "sg_exchange_wait_reduce")
     end
 end
+# Support-plane (halo) variant: planes go to the ranks whose slabs read them, the barrier involves those neighbours only, and
+# grad is written on this rank's support planes k0s[my_rank+1] .. k0s[my_rank+1] + nps[my_rank+1] - 1 (0-based) only.
+function adjoint_push_support!(plan::AdjointPlan, cp::CuArray{Float64}, eval::CuArray{Float64}, workspace::CuVector{UInt8},
+        peer_stage::Vector{Ptr{Cvoid}}, my_rank::Integer, k0s::Vector{Int64}, nps::Vector{Int64}, max_planes::Integer;
+        keep_local::Bool = false)
+    GC.@preserve plan cp eval workspace peer_stage k0s nps begin
+        check(ccall((:sg_evaluate_adjoint_planned_support_f64, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Ptr{Ptr{Cvoid}}, Cint, Cint, Ptr{Int64},
+                     Ptr{Int64}, Int64, Cint, Ptr{Cvoid}),
+                    plan.handle, devptr(cp), devptr(eval), C_NULL, devptr(workspace), length(workspace), peer_stage, length(peer_stage),
+                    my_rank, k0s, nps, max_planes, keep_local, stream_ptr()), "sg_evaluate_adjoint_planned_support")
+    end
+end
+function exchange_wait_reduce_support!(grad::CuArray{Float64}, my_stage::CuArray{Float64}, my_flags::CuVector{UInt64},
+        local_sync::CuVector{UInt8}, peer_flags::Vector{Ptr{Cvoid}}, my_rank::Integer, k0s::Vector{Int64}, nps::Vector{Int64},
+        max_planes::Integer)
+    world = length(peer_flags)
+    plane_elems = prod(size(grad)[1:(ndims(grad) - 2)])
+    GC.@preserve grad my_stage my_flags local_sync peer_flags k0s nps begin
+        check(ccall((:sg_exchange_wait_reduce_support_f64, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Cint, Cint, Ptr{Int64}, Ptr{Int64}, Int64, Int64, Cint,
+                     Int64, Ptr{Cvoid}),
+                    devptr(grad), devptr(my_stage), devptr(my_flags), devptr(local_sync), peer_flags, world, my_rank, k0s, nps,
+                    plane_elems, size(grad, ndims(grad) - 1), size(grad, ndims(grad)), max_planes, stream_ptr()),
+              "sg_exchange_wait_reduce_support")
+    end
+end
 # A whole iteration (evaluate!, adjoint_push!, exchange_wait_reduce!) can be wrapped in CUDA.@captured: the library only
 # enqueues kernels, the barrier between the ranks is a device-side flag wait.
 
