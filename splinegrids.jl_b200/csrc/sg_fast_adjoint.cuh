@@ -251,11 +251,8 @@ __global__ void __launch_bounds__(128) sg_adj_march_kernel(const __grid_constant
     };
 
     // one marching step: sample s of the staged piece, values x[NT][V]
-    auto step = [&](int s, T (&x)[NT][V]) {
-        const int sp = ss[s];
-        if (cur < sp) {
-            do emit_oldest(); while (cur < sp);
-        }
+    // the accumulation of one sample row of span `cur` (no span bookkeeping)
+    auto accumulate = [&](int s, T (&x)[NT][V]) {
         T b[P + 1];
 #pragma unroll
         for (int k = 0; k <= P; ++k) b[k] = bs[s * (P + 1) + k];
@@ -276,6 +273,13 @@ __global__ void __launch_bounds__(128) sg_adj_march_kernel(const __grid_constant
             for (int k = 0; k <= P; ++k)
 #pragma unroll
                 for (int v = 0; v < V; ++v) acc[t][v][k] = fma(b[k], x[t][v], acc[t][v][k]);
+    };
+    auto step = [&](int s, T (&x)[NT][V]) {
+        const int sp = ss[s];
+        if (cur < sp) {
+            do emit_oldest(); while (cur < sp);
+        }
+        accumulate(s, x);
     };
 
     for (int64_t jp = j_lo; jp < j_hi; jp += SG_ADJ_PIECE) {
@@ -298,8 +302,13 @@ __global__ void __launch_bounds__(128) sg_adj_march_kernel(const __grid_constant
                 for (int t = 0; t < NT; ++t) sg_load_vec<T, V>(xp + x_ch * t, xs[u][t]);
                 xp += inner;
             }
+            if (ss[s + U - 1] == cur) {   // block-uniform: the whole batch lies in the current span (indices are monotone)
 #pragma unroll
-            for (int u = 0; u < U; ++u) step(s + u, xs[u]);
+                for (int u = 0; u < U; ++u) accumulate(s + u, xs[u]);
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) step(s + u, xs[u]);
+            }
         }
         for (; s < np; ++s) {   // tail
             T x1[NT][V];
