@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(128, 4) sg_adj_post2_kernel(T *__restrict__ cp
                                                            const int32_t *__restrict__ index1, const int32_t *__restrict__ g_lo,
                                                            const T *__restrict__ g_w, const SgAdjointHeader *hdr, int64_t n1, int64_t c1, int64_t c2, int64_t c3, int P1,
                                                            int tiles2, int G3, int chunks3, int path,
-                                                           const __grid_constant__ SgPushSpec push, int discard, int sf_known, int sl_known)
+                                                           const __grid_constant__ SgPushSpec push, int discard, int sf_known, int sl_known, int i3_top)
 {
     constexpr int S = G2 + P;
     constexpr int JMAX = SG_POST2_JMAX;
@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(128, 4) sg_adj_post2_kernel(T *__restrict__ cp
     const int t = (int)(blockIdx.x % (unsigned)(tiles2 + 1));          // tile of dimension 2 (tiles2 = the last tile's halo rows)
     const int64_t ib = blockIdx.x / (unsigned)(tiles2 + 1);            // block of control indices of dimension 1
     // planes in DESCENDING order: the march kernel wrote the high planes last, they are the ones still in L2
-    const int64_t i3 = (int64_t)(gridDim.y - blockIdx.y);              // 1-based control index of dimension 3
+    // (i3_top = c3 with gridDim.y = c3: every plane; a push-only call launches the planes of the slab's support only)
+    const int64_t i3 = (int64_t)i3_top - blockIdx.y;                    // 1-based control index of dimension 3
     const int64_t o = blockIdx.z;
     const int64_t i2_0 = (int64_t)t * G2;                               // 0-based control row of slot 0
     if (i2_0 >= c2) return;

@@ -658,14 +658,23 @@ static int sg_run_march2(T *cp, const SgGridArgs<T> &a, const SgSpanStarts<T> &s
         dim3 pgrid((unsigned)((mp.tiles2 + 1) * sg_blocks(a.n_cp[0], 128)), (unsigned)m.c3, (unsigned)a.nout);
         SgPushSpec ps{};                                                // world == 0: plain adjoint
         if (g_sg_push != nullptr) { ps = *g_sg_push; g_sg_push_done = true; }
+        // A planned call that only PUSHES (keep_local == 0: nothing is written outside the slab's support) launches the planes
+        // of the support only: on an 8-way slab 19 of 128 planes, i.e. 85 % of the CTAs would load their tables and exit.
+        int i3_top = (int)m.c3;
+        if (known.planned && known.sf3 > 0 && ps.world > 0 && ps.keep_local == 0) {
+            i3_top = (int)std::min<int64_t>(known.sl3, m.c3);
+            const int i3_bot = std::max(known.sf3 - P, 1);
+            if (i3_top < i3_bot) return SG_OK;
+            pgrid.y = (unsigned)(i3_top - i3_bot + 1);
+        }
         // drop the partials' dirty L2 lines after their only read: needs whole 128-byte lines per row (n1 a multiple of a
         // line) and ONE block of control indices (c1 <= 128), else neighbouring blocks read overlapping sample ranges
         const int discard = sg_env_int("SG_ADJ_DISCARD", 1) && (m.n1 * sizeof(T)) % 128 == 0 && reinterpret_cast<uintptr_t>(part) % 128 == 0 &&
                             a.n_cp[0] <= 128;
         switch (P) {
-            case 1: sg_adj_post2_kernel<T, 1, SG_M2_G2><<<pgrid, 128, 0, st>>>(cp, part, a.table[0], a.index[0], ss.g_lo, ss.g_w, hdr, m.n1, a.n_cp[0], m.c2, m.c3, a.degree[0], mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS, ps, discard, known.sf3, known.sl3); break;
-            case 2: sg_adj_post2_kernel<T, 2, SG_M2_G2><<<pgrid, 128, 0, st>>>(cp, part, a.table[0], a.index[0], ss.g_lo, ss.g_w, hdr, m.n1, a.n_cp[0], m.c2, m.c3, a.degree[0], mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS, ps, discard, known.sf3, known.sl3); break;
-            default: sg_adj_post2_kernel<T, 3, SG_M2_G2><<<pgrid, 128, 0, st>>>(cp, part, a.table[0], a.index[0], ss.g_lo, ss.g_w, hdr, m.n1, a.n_cp[0], m.c2, m.c3, a.degree[0], mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS, ps, discard, known.sf3, known.sl3); break;
+            case 1: sg_adj_post2_kernel<T, 1, SG_M2_G2><<<pgrid, 128, 0, st>>>(cp, part, a.table[0], a.index[0], ss.g_lo, ss.g_w, hdr, m.n1, a.n_cp[0], m.c2, m.c3, a.degree[0], mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS, ps, discard, known.sf3, known.sl3, i3_top); break;
+            case 2: sg_adj_post2_kernel<T, 2, SG_M2_G2><<<pgrid, 128, 0, st>>>(cp, part, a.table[0], a.index[0], ss.g_lo, ss.g_w, hdr, m.n1, a.n_cp[0], m.c2, m.c3, a.degree[0], mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS, ps, discard, known.sf3, known.sl3, i3_top); break;
+            default: sg_adj_post2_kernel<T, 3, SG_M2_G2><<<pgrid, 128, 0, st>>>(cp, part, a.table[0], a.index[0], ss.g_lo, ss.g_w, hdr, m.n1, a.n_cp[0], m.c2, m.c3, a.degree[0], mp.tiles2, mp.G3, mp.chunks3, SG_PATH_MULTIPASS, ps, discard, known.sf3, known.sl3, i3_top); break;
         }
         g_sg_launches.fetch_add(1);
         return SG_OK;
