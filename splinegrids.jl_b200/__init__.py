@@ -14,7 +14,8 @@ from .config import adjoint_plans, asynchronous, is_synchronous, set_adjoint_pla
 from .control_points import (DefaultControlPoints, LocallyRefinedControlPoints, LocalRefinement,
                              activate_local_control_point_range_, activate_local_refinement_, copyto_,
                              deactivate_overwritten_control_points_, get_n_control_points, obtain)
-from .distributed import PeerGradientExchange, SlabShardedGrid, allreduce_gradient_, slab_bounds
+from .distributed import (PeerGradientExchange, SlabShardedGrid, allgather_support_planes_, allreduce_gradient_, owned_planes,
+                          slab_bounds, slab_supports)
 from .graphs import CapturedCalls
 from .knot_vector import KnotVector
 from .linear_map import SplineGridLinearMap
@@ -32,7 +33,7 @@ __all__ = [
     "rmeye", "refinement_matrix_from_dense", "decompress", "set_sample_indices_", "build_", "insert_knot", "refine",
     "add_default_local_refinement", "activate_local_refinement_", "activate_local_control_point_range_",
     "deactivate_overwritten_control_points_", "error_informed_local_refinement_", "get_n_control_points", "obtain",
-    "copyto_", "SplineGridLinearMap", "SlabShardedGrid", "PeerGradientExchange", "allreduce_gradient_", "slab_bounds", "to_device", "to_numpy",
+    "copyto_", "SplineGridLinearMap", "SlabShardedGrid", "PeerGradientExchange", "allreduce_gradient_", "slab_bounds", "slab_supports", "owned_planes", "allgather_support_planes_", "to_device", "to_numpy",
     "jl_zeros", "jl_ones", "jl_empty", "reshape_colmajor", "is_colmajor", "as_colmajor", "set_synchronous",
     "is_synchronous", "asynchronous", "set_kernel_policy", "last_variant", "launch_count", "launch_count_reset",
     "SplineGridsError", "SplineGridsB200Error", "boehm_refinement_matrix", "CapturedCalls", "set_adjoint_plans",

@@ -57,6 +57,53 @@ def allreduce_gradient_(control_points: torch.Tensor, group=None) -> torch.Tenso
     return control_points
 
 
+def slab_supports(last: SplineDimension, world_size: int) -> Tuple[list, list]:
+    """Control planes of the slowest axis every rank's slab touches: ``(k0s, nps)``, 0-based first plane and number of
+    planes per rank.  A slab with sample rows ``[lo, hi)`` reads / contributes to the planes ``idx[lo] - p - 1 ..
+    idx[hi - 1] - 1`` (0-based; ``idx`` = the 1-based span indices, src/spline_grid.jl:130-182 window offset)."""
+    idx = last.sample_indices.cpu().numpy()
+    p = last.degree
+    k0s, nps = [], []
+    for r in range(world_size):
+        lo, hi = slab_bounds(last.n_sample_points, world_size, r)
+        k0 = int(idx[lo]) - p - 1
+        k0s.append(k0)
+        nps.append(int(idx[hi - 1]) - k0)
+    return k0s, nps
+
+
+def owned_planes(k0s: Sequence[int], nps: Sequence[int], rank: int) -> Tuple[int, int]:
+    """The part ``[lo, hi)`` of rank's support below the first plane of the next rank's support:
+    ``[k0_r, min(k0_{r+1}, k0_r + np_r))`` (the last rank owns its whole support).  The owned ranges are disjoint and their
+    union is the union of the supports, so they say who contributes which plane when the replicated array is rebuilt."""
+    lo = k0s[rank]
+    hi = k0s[rank] + nps[rank]
+    if rank + 1 < len(k0s):
+        hi = min(hi, max(k0s[rank + 1], lo))
+    return lo, hi
+
+
+def allgather_support_planes_(control_points: torch.Tensor, k0s: Sequence[int], nps: Sequence[int], group=None) -> torch.Tensor:
+    """After a fit that used the support-plane exchange every rank holds valid control points on ITS support planes only;
+    this rebuilds the replicated array: every rank broadcasts the planes it owns (``owned_planes``).  One call at the END of
+    a fit (plumbing through ``torch.distributed``), not part of the step."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return control_points
+    world = dist.get_world_size(group)
+    me = dist.get_rank(group)
+    for r in range(world):
+        lo, hi = owned_planes(k0s, nps, r)
+        if hi <= lo:
+            continue
+        view = control_points[..., lo:hi, :]
+        buf = view.contiguous() if r == me else torch.empty(view.shape, dtype=view.dtype, device=view.device)
+        dist.broadcast(buf, src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+        if r != me:
+            view.copy_(buf)
+    return control_points
+
+
 class PeerGradientExchange:
     """Gradient exchange over NVLink peer memory (replaces the all-reduce).
 
@@ -85,14 +132,7 @@ class PeerGradientExchange:
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
         last = global_dims[-1]
-        idx = last.sample_indices.cpu().numpy()
-        p = last.degree
-        self.k0, self.np_ = [], []
-        for r in range(world_size):
-            lo, hi = slab_bounds(last.n_sample_points, world_size, r)
-            k0 = int(idx[lo]) - p - 1
-            self.k0.append(k0)
-            self.np_.append(int(idx[hi - 1]) - k0)
+        self.k0, self.np_ = slab_supports(last, world_size)
         self.rank, self.world = rank, world_size
         self.c_last = last.n_basis_functions
         self.plane_elems = int(np.prod([sd.n_basis_functions for sd in global_dims[:-1]])) if len(global_dims) > 1 else 1
@@ -162,6 +202,10 @@ class PeerGradientExchange:
         """0-based control planes ``[lo, hi)`` of the slowest axis that rank's slab touches (= reads in ``evaluate!``)."""
         r = self.rank if rank is None else rank
         return self.k0[r], self.k0[r] + self.np_[r]
+
+    def allgather_support_planes_(self, control_points: torch.Tensor, group=None) -> torch.Tensor:
+        """Rebuild the replicated control-point array after a fit with the support-plane exchange (see the module function)."""
+        return allgather_support_planes_(control_points, self.k0, self.np_, group)
 
     def exchange_(self, grad: torch.Tensor) -> torch.Tensor:
         """Push kernel + (signal, wait, reduce) kernel on an already computed local partial gradient."""

@@ -52,14 +52,32 @@ def _worker(rank: int, world_size: int, port: int, out_dir: str):
                                     n_cp + (nout,))
         err = np.linalg.norm(t.numpy() - g_full) / np.linalg.norm(g_full)
         assert err < 1e-13, err
+        # support-plane exchange, host side: supports of all ranks, owned ranges, end-of-fit all-gather.  The exchange kernels
+        # need GPUs (tests/test_gpu_parity.py, test_gpu_multiproc.py); their RESULT is emulated here: the summed gradient on
+        # this rank's support planes, NaN elsewhere.
+        from types import SimpleNamespace
+        last = SimpleNamespace(sample_indices=torch.from_numpy(dims[-1].sample_indices.astype(np.int32)), degree=deg[-1],
+                               n_sample_points=n_s[-1])
+        k0s, nps = S.slab_supports(last, world_size)
+        assert (k0s[rank], k0s[rank] + nps[rank]) == (k0, k1)
+        owned = [S.owned_planes(k0s, nps, r) for r in range(world_size)]
+        covered = sorted(k for lo_, hi_ in owned for k in range(lo_, hi_))
+        assert covered == sorted(set(covered))                                   # disjoint
+        assert set(covered) == {k for a, n in zip(k0s, nps) for k in range(a, a + n)}   # union of the supports
+        assert all(k0s[r] <= owned[r][0] and owned[r][1] <= k0s[r] + nps[r] for r in range(world_size))
+        g_sup = torch.full_like(t, float("nan"))
+        g_sup[..., k0:k1, :] = t[..., k0:k1, :]
+        S.allgather_support_planes_(g_sup, k0s, nps)
+        assert set(covered) == set(range(n_cp[-1])) and np.array_equal(g_sup.numpy(), t.numpy())
         Path(out_dir, f"ok{rank}").write_text(f"{err}")
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.timeout(300)
-def test_slab_sharded_adjoint_allreduce_world_size_2(tmp_path):
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_sharded_adjoint_allreduce_world_size_2(tmp_path, world):
     import torch.multiprocessing as mp
-    port = 29500 + os.getpid() % 2000
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+    port = 29500 + (os.getpid() + 7 * world) % 2000
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))

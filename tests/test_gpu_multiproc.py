@@ -129,6 +129,10 @@ def _worker(rank: int, world: int, port: int, out_dir: str):
             assert torch.equal(grad[:, :, lo:hi, :], full_grad[:, :, lo:hi, :]), it     # same bits as the replicated exchange
             assert bool(torch.isnan(grad[:, :, :lo, :]).all()) and bool(torch.isnan(grad[:, :, hi:, :]).all())
         assert not sh2.exchange.status()[1]
+        # end of a fit: the replicated array is rebuilt from the planes every rank owns (NCCL broadcasts)
+        sh2.exchange.allgather_support_planes_(grad)
+        torch.cuda.synchronize()
+        assert torch.equal(grad, full_grad)
         Path(out_dir, f"ok{rank}").write_text("ok")
     finally:
         dist.destroy_process_group()
