@@ -578,6 +578,11 @@ def main_gpu(args):
                 "config": {"workload": w["name"], "step": "evaluate! + evaluate_adjoint! (+ NCCL all-reduce of the gradient for N>1)",
                            "sharding": f"sample grid in {world} slab(s) along axis 3, control points replicated",
                            "gradient_exchange": sh.exchange_kind, "exchange_check": exchange_check,
+                           "exchange_mode": (None if world == 1 else ("nccl_allreduce" if sh.exchange is None else sh.exchange.mode)),
+                           "exchange_note": (None if world == 1 or sh.exchange is None or sh.exchange.mode != "support" else
+                                             "every rank ends the step with the summed gradient on the control planes its own slab "
+                                             "reads (what the next evaluate! needs); --exchange replicated gives every rank the whole "
+                                             "gradient (profiles/r02_bench_n{2,4,8}.json: 0.255 / 0.159 / 0.115 ms per step)"),
                            "nvls_multicast_push": bool(sh.exchange is not None and any(sh.exchange.mc_ptrs)),
                            "launch": ("CUDA graph of the step's kernels (2 steps per replay)" if cap is not None
                                       else "eager" + (f" (graph capture failed: {cap_err})" if cap_err else "")),
