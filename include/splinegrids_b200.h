@@ -381,6 +381,9 @@ int sg_exchange_wait_reduce_f64(double *grad, const double *stage, const void *m
  * untouched.  Per-rank NVLink ingress drops from (world - 1)/world of the gradient to the halo planes.  Same staging layout,
  * flags, local_sync and two-buffer rule as above; every rank must use the same variant in a given exchange.  k0s / nps: HOST
  * arrays of `world` entries.  Pipelines without the fused push fall back to a push of all planes to all ranks (correct). */
+/* host-only helper (no device needed): which LOCAL planes [dst_lo[r], dst_hi[r]) of rank my_rank's support go to rank r */
+int sg_exchange_support_ranges(int world, int my_rank, const int64_t *k0s, const int64_t *nps, int64_t max_planes,
+                               int *dst_lo, int *dst_hi);
 int sg_evaluate_adjoint_planned_support_f32(const sg_adjoint_plan *plan, float *cp, const float *eval, const float *weights_or_null,
                                             void *workspace, size_t workspace_bytes, void *const *peer_stage, int world,
                                             int my_rank, const int64_t *k0s, const int64_t *nps, int64_t max_planes,

@@ -343,6 +343,25 @@ extern "C" int sg_adjoint_plan_info(const sg_adjoint_plan *plan, int *monotone, 
     return SG_OK;
 }
 
+// Support-plane exchange, host side (pure host code, no device needed): the LOCAL planes [dst_lo[r], dst_hi[r]) of rank my_rank's
+// support that rank r's slab touches too, i.e. the overlap of the two supports (ranks whose supports do not meet receive nothing;
+// the own slot always gets every plane).
+extern "C" int sg_exchange_support_ranges(int world, int my_rank, const int64_t *k0s, const int64_t *nps, int64_t max_planes,
+                                          int *dst_lo, int *dst_hi)
+{
+    if (!k0s || !nps || !dst_lo || !dst_hi || world < 1 || world > SG_MAX_PEERS || my_rank < 0 || my_rank >= world || max_planes < 0)
+        return SG_ERR_INVALID_ARGUMENT;
+    const int full = (int)std::min<int64_t>(max_planes, INT32_MAX);
+    for (int r = 0; r < world; ++r) {
+        if (r == my_rank) { dst_lo[r] = 0; dst_hi[r] = full; continue; }
+        const int64_t lo = std::max(k0s[r], k0s[my_rank]) - k0s[my_rank];
+        const int64_t hi = std::min(k0s[r] + nps[r], k0s[my_rank] + nps[my_rank]) - k0s[my_rank];
+        dst_lo[r] = (int)std::min<int64_t>(std::max<int64_t>(lo, 0), full);
+        dst_hi[r] = (int)std::max<int64_t>(std::min<int64_t>(hi, full), dst_lo[r]);
+    }
+    return SG_OK;
+}
+
 extern "C" int sg_exchange_push_f32(const float *, void *const *, int, int, int64_t, int64_t, int, int64_t, int64_t, int64_t, void *);
 extern "C" int sg_exchange_push_f64(const double *, void *const *, int, int, int64_t, int64_t, int, int64_t, int64_t, int64_t, void *);
 
@@ -363,15 +382,8 @@ static int sg_adjoint_push_impl(const sg_adjoint_plan *plan, T *cp, int nin, con
     spec.n_dst = world;
     for (int r = 0; r < SG_MAX_PEERS; ++r) { spec.dst_lo[r] = 0; spec.dst_hi[r] = (int)std::min<int64_t>(max_planes, INT32_MAX); }
     if (k0s && nps) {
-        // support-plane exchange: rank r only needs the planes its own slab touches, i.e. the overlap of the two supports
-        // (ranks whose supports do not meet receive nothing); the own slot always gets every plane
-        for (int r = 0; r < world; ++r) {
-            if (r == my_rank) continue;
-            const int64_t lo = std::max(k0s[r], k0s[my_rank]) - k0s[my_rank];
-            const int64_t hi = std::min(k0s[r] + nps[r], k0s[my_rank] + nps[my_rank]) - k0s[my_rank];
-            spec.dst_lo[r] = (int)std::max<int64_t>(lo, 0);
-            spec.dst_hi[r] = (int)std::max<int64_t>(std::min<int64_t>(hi, max_planes), spec.dst_lo[r]);
-        }
+        int rc = sg_exchange_support_ranges(world, my_rank, k0s, nps, max_planes, spec.dst_lo, spec.dst_hi);
+        if (rc != SG_OK) return rc;
     } else if (multicast_stage != nullptr) { spec.stage[0] = multicast_stage; spec.n_dst = 1; }   // one store reaches every rank
     g_sg_push = &spec; g_sg_push_done = false;
     int rc = sg_evaluate_adjoint_impl<T>(cp, nin, n_samples, n_cp, nout, tables, indices, degree, mdo, der, eval, weights,

@@ -114,6 +114,34 @@ def test_slab_bounds_partition(S):
     assert S.slab_bounds(512, 8, 3) == (192, 256)
 
 
+def test_support_plane_ranges_host_side(S):
+    """sg_exchange_support_ranges (pure host code): which local planes of a rank's support go to which rank in the
+    support-plane gradient exchange -- the overlap of the two supports, everything into the own slot, nothing to ranks
+    whose slabs do not share a plane; and the owned ranges used by the end-of-fit all-gather."""
+    import ctypes as C
+    lib = S._lib.lib()
+    k0, npl = [0, 5, 11, 17], [8, 9, 9, 6]                     # supports [0,8) [5,14) [11,20) [17,23): neighbours share 3 planes
+    world, max_planes = 4, max(npl)
+    k0s, nps = S._lib.i64_array(k0), S._lib.i64_array(npl)
+    expect = {0: [(0, 9), (5, 8), (8, 8), (8, 8)],             # local plane l of rank r is global plane k0[r] + l
+              1: [(0, 3), (0, 9), (6, 9), (9, 9)],
+              2: [(0, 0), (0, 3), (0, 9), (6, 9)],
+              3: [(0, 0), (0, 0), (0, 3), (0, 9)]}
+    for r in range(world):
+        lo, hi = (C.c_int * 16)(), (C.c_int * 16)()
+        assert lib.sg_exchange_support_ranges(C.c_int(world), C.c_int(r), k0s, nps, C.c_int64(max_planes), lo, hi) == 0
+        got = [(lo[q], hi[q]) for q in range(world)]
+        for q in range(world):
+            planes = set(range(k0[r] + got[q][0], k0[r] + got[q][1]))
+            if q == r:
+                assert got[q] == (0, max_planes)
+            else:                                                # exactly the planes both supports contain
+                assert planes == set(range(k0[r], k0[r] + npl[r])) & set(range(k0[q], k0[q] + npl[q])), (r, q, got)
+        assert [b - a for a, b in got] == [b - a for a, b in expect[r]]
+    assert lib.sg_exchange_support_ranges(C.c_int(4), C.c_int(4), k0s, nps, C.c_int64(9), lo, hi) != 0   # bad rank
+    assert [S.owned_planes(k0, npl, r) for r in range(world)] == [(0, 5), (5, 11), (11, 17), (17, 23)]
+
+
 def test_bench_reference_arm_contract_line():
     """`bench.py --impl reference` (the CPU arm: the oracle on the host cores) prints ONE JSON line with the contract keys,
     for the default workload and for another BASELINE config; all host threads are used whatever OMP_NUM_THREADS says."""
