@@ -142,6 +142,36 @@ def test_support_plane_ranges_host_side(S):
     assert [S.owned_planes(k0, npl, r) for r in range(world)] == [(0, 5), (5, 11), (11, 17), (17, 23)]
 
 
+def test_slab_supports_and_owned_planes_random_layouts(S):
+    """slab_supports / owned_planes on random monotone span-index arrays (irregular sample spacing, thin slabs whose
+    supports reach past the direct neighbour): a rank's support is exactly the set of control planes its rows touch, the owned
+    ranges are disjoint, lie inside the supports and cover the union of the supports."""
+    import torch
+    from types import SimpleNamespace
+    rng = np.random.default_rng(3)
+    for trial in range(200):
+        p = int(rng.integers(1, 5))
+        c = int(rng.integers(p + 1, 40))
+        n = int(rng.integers(1, 60))
+        world = int(rng.integers(1, min(n, 8) + 1))
+        idx = np.sort(rng.integers(p + 1, c + 1, size=n)).astype(np.int32)      # 1-based span indices in [p + 1, c]
+        last = SimpleNamespace(sample_indices=torch.from_numpy(idx), degree=p, n_sample_points=n)
+        k0s, nps = S.slab_supports(last, world)
+        union = set()
+        for r in range(world):
+            lo, hi = S.slab_bounds(n, world, r)
+            touched = {int(i) - p - 1 + a for i in idx[lo:hi] for a in range(p + 1)}
+            sup = set(range(k0s[r], k0s[r] + nps[r]))
+            assert touched <= sup and min(touched) == k0s[r] and max(touched) == k0s[r] + nps[r] - 1
+            assert 0 <= k0s[r] and k0s[r] + nps[r] <= c
+            union |= sup
+        owned = [S.owned_planes(k0s, nps, r) for r in range(world)]
+        flat = [k for lo, hi in owned for k in range(lo, hi)]
+        assert len(flat) == len(set(flat)), (trial, owned)
+        assert set(flat) == union, (trial, k0s, nps, owned)
+        assert all(k0s[r] <= lo and hi <= k0s[r] + nps[r] for r, (lo, hi) in enumerate(owned))
+
+
 def test_bench_reference_arm_contract_line():
     """`bench.py --impl reference` (the CPU arm: the oracle on the host cores) prints ONE JSON line with the contract keys,
     for the default workload and for another BASELINE config; all host threads are used whatever OMP_NUM_THREADS says."""
